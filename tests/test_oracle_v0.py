@@ -1,0 +1,129 @@
+"""Pins the C oracle (oracle/futbol_v0_oracle.c) to the reference.
+
+Golden vectors come from the unmodified reference (tests/golden/make_golden_v0.py); the
+known-answer numbers of test_appendix_a_* are the ones printed in SURVEY.md Appendix A.
+Bar: every integer output and the draw count exact; floats BIT-exact (the oracle computes
+in the reference's operation order with the same libm).
+"""
+import numpy as np
+import pytest
+
+from oracle import philox
+from oracle.v0 import OracleV0, lib
+
+INT_FIELDS = ("done", "owner", "last_owner", "ai_score", "opp_score")
+
+
+def _run_case(case, sq_mode=1):
+    m = case["meta"]
+    kw = m["kwargs"]
+    o = OracleV0(1, seed=m["seed"], env_id0=m["env_id"], random_opp=m["random_opp"], sq_mode=sq_mode,
+                 rng_const=(m["rng"] == "const"), one_goal_end=kw.get("one_goal_end", False),
+                 only_reward_goal=kw.get("only_reward_goal", False), game_time=kw.get("game_time", 40.0))
+    return o.rollout(m["steps"], actions=case["action"], autoreset=1)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    assert philox.philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+    assert philox.philox4x32_10((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2) == (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
+    assert philox.philox4x32_10((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0)) == \
+        (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)
+    ctr = np.array([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], np.uint32)
+    key = np.array([0xA4093822, 0x299F31D0], np.uint32)
+    out = np.zeros(4, np.uint32)
+    lib().futbol_oracle_philox(ctr.ctypes.data, key.ctypes.data, out.ctypes.data)
+    assert out.tolist() == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_action_stream_matches_python():
+    from oracle.v0 import action_for
+    tab = philox.actions_table(11, np.arange(5, 9), 3, 50)
+    for j, e in enumerate(range(5, 9)):
+        for t in range(3, 53):
+            a = philox.action_for(11, e, t)
+            assert a == action_for(11, e, t) == tab[t - 3, j]
+
+
+def test_oracle_matches_reference_golden_bit_exact(golden_v0):
+    """Floats are required BIT-exact when this box's libm pow() reproduces the fingerprint stored with
+    the vectors (numpy-scalar x**2 is libm pow, which is not correctly rounded); otherwise 1e-12."""
+    cases, same_libm = golden_v0["cases"], golden_v0["same_libm"]
+    assert len(cases) >= 40
+    for name, case in cases.items():
+        out = _run_case(case)
+        for f in INT_FIELDS:
+            assert np.array_equal(out[f][:, 0], case[f]), (name, f)
+        if case["meta"]["rng"] == "philox":
+            assert np.array_equal(out["draws"][:, 0].astype(np.int64), case["draws"]), name
+        steps = case["meta"]["steps"]
+        ref = case["obs"].reshape(steps, 30)
+        if same_libm:
+            assert np.array_equal(out["obs"][:, 0], ref), name
+        else:
+            assert (np.abs(out["obs"][:, 0] - ref) <= 1e-12 * np.maximum(1.0, np.abs(ref))).all(), name
+        assert np.array_equal(out["reward"][:, 0], case["reward"]), name
+
+
+def test_oracle_kernel_arithmetic_mode_within_tolerance(golden_v0):
+    """sq_mode=0 (x*x, what the CUDA kernel computes) vs the reference: ints exact, floats 1e-9."""
+    worst = 0.0
+    for name, case in golden_v0["cases"].items():
+        out = _run_case(case, sq_mode=0)
+        for f in INT_FIELDS:
+            assert np.array_equal(out[f][:, 0], case[f]), (name, f)
+        steps = case["meta"]["steps"]
+        ref = case["obs"].reshape(steps, 30)
+        err = np.abs(out["obs"][:, 0] - ref) / np.maximum(1.0, np.abs(ref))
+        worst = max(worst, float(err.max()))
+    assert worst <= 1e-9
+
+
+def test_appendix_a_known_answers():
+    """Numbers transcribed from SURVEY.md Appendix A (constant RNG, random_opp=False)."""
+    acts = [0] * 9 + [5] + [0] * 6 + [10] + [0] * 3 + [15, 4, 1, 0, 0, 2, 8, 0, 0, 0]
+    o = OracleV0(1, random_opp=False, rng_const=True)
+    out = o.rollout(30, actions=np.array(acts, np.uint8), autoreset=1)
+    rewards = [2, 2, 2, 2, 2, 2, 2, 2, 2, 18, 13, 13, 13, 13, 13, 13, -1, 2, 2, 2, -2, 20, 2, 13, 4, 1, 1, 2, 2, 2]
+    N, O2, A1, A2 = 4, 3, 0, 1
+    owners = [N] * 8 + [O2] + [A2] * 7 + [N] * 3 + [O2, O2, A1, A2, A2] + [O2] * 6
+    assert out["reward"][:, 0].tolist() == [float(r) for r in rewards]
+    assert out["owner"][:, 0].tolist() == owners
+    assert not out["done"].any() and out["ai_score"].max() == 0 and out["opp_score"].max() == 0
+    hexes = ["0x1.ca5cdc1ec1dfep+5", "0x1.154bc5377189ap+5", "-0x1.ad32ede641040p+0", "0x1.ba78baaf8fb80p+0", "0x1.8p+3",
+             "0x1.c50f5a3f72476p+5", "0x1.1ad221e829e96p+5", "-0x1.07e9df0117d00p+0", "0x1.05518015d2600p+0", "0x1.8p+3"]
+    assert out["obs"][29, 0, :10].tolist() == [float.fromhex(h) for h in hexes]
+    # step 9: both opponents intercept in one step (Q11); last owner = OPP_1
+    assert out["last_owner"][8, 0] == 2 and out["owner"][8, 0] == 3
+
+
+def test_episode_length_and_reset():
+    """First done=True on step 401 (SURVEY.md a13 / BASELINE.md section 2)."""
+    o = OracleV0(3, seed=9, env_id0=100, random_opp=True)
+    out = o.rollout(900, autoreset=1)
+    for i in range(3):
+        assert np.flatnonzero(out["done"][:, i]).tolist() == [400, 801]
+    # the reset obs after construction: kickoff rows, owner row all zeros
+    o2 = OracleV0(1)
+    obs = o2.envs["obs"][0]
+    assert obs[4].tolist() == [52.5, 34.0, 0, 0, 0] and obs[0].tolist() == [43.5, 39.0, 0, 0, 0]
+    assert obs[3].tolist() == [61.5, 29.0, 0, 0, 0] and not obs[5].any()
+
+
+def test_vec_semantics_and_threads_agree():
+    a = OracleV0(64, seed=5, env_id0=10, random_opp=False, game_time=3.0)
+    b = OracleV0(64, seed=5, env_id0=10, random_opp=False, game_time=3.0)
+    oa = a.rollout(100, autoreset=2, n_threads=1)
+    ob = b.rollout(100, autoreset=2, n_threads=4)
+    for k in oa:
+        assert np.array_equal(oa[k], ob[k]), k
+    t, i = np.argwhere(oa["done"])[0]
+    assert oa["obs"][t, i, 20:25].tolist() == [52.5, 34.0, 0, 0, 0]   # reset obs in the done slot
+    assert not oa["obs"][t, i, 25:].any()
+
+
+def test_trajectory_independent_of_batch_position():
+    big = OracleV0(32, seed=3, env_id0=1000, random_opp=False).rollout(200)
+    one = OracleV0(1, seed=3, env_id0=1017, random_opp=False).rollout(200)
+    assert np.array_equal(big["obs"][:, 17], one["obs"][:, 0])
+    assert np.array_equal(big["reward"][:, 17], one["reward"][:, 0])
