@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/s of the v0 FutbolEnv step, 2v2 vs hard-coded opponents, 2^20 envs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One bench "step" = one fused rollout launch: every env of the job advanced ROLLOUT_K = 64 env-steps
+(BASELINE.json configs[2]).  The 2^20 envs of the metric are sharded over the N ranks by global env
+id (no data-path collective), so total work is fixed as N grows: "scaling": "strong".
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TOTAL_ENVS = 1 << 20
+ROLLOUT_K = 64
+STATE_BYTES_PER_ENV = 223                      # SoA state, v0_kernels.cu
+BYTES_PER_ENV_STEP = 120 + 4 + 1 + 1 + 2.0 * STATE_BYTES_PER_ENV / ROLLOUT_K   # obs f32x30, reward, done, action, state/K
+METRIC = "env-steps/sec (whole box) 2v2 at 2^20 envs"
+UNIT = "env-steps/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+# ----------------------------------------------------------------------------------- CPU legs
+def cpu_port_baseline(budget_s=12.0, threads=None):
+    """The C oracle port (oracle/futbol_v0_oracle.c) on all host cores, bounded sample of the same workload."""
+    from oracle.v0 import OracleV0
+    threads = threads or os.cpu_count() or 1
+    n = 8192
+    orc = OracleV0(n, seed=0, random_opp=False, arith=0)
+    orc.rollout(ROLLOUT_K, autoreset=2, n_threads=threads, record=False)      # warm-up
+    t0, steps = time.perf_counter(), 0
+    while time.perf_counter() - t0 < budget_s:
+        orc.rollout(ROLLOUT_K, autoreset=2, n_threads=threads, record=False)
+        steps += n * ROLLOUT_K
+    dt = time.perf_counter() - t0
+    return {"value": steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d envs x %d env-steps (%d rollouts of K=%d) in %.1f s, random_opp=False, C oracle, %d pthreads"
+                      % (n, steps // n, steps // (n * ROLLOUT_K), ROLLOUT_K, dt, threads)}
+
+
+def _py_ref_worker(widx, n_envs, env_steps, q_in, q_out):
+    from oracle.ref_harness import RefEnvV0
+    import random
+    envs = [RefEnvV0(seed=widx, env_id=i, random_opp=False, rng="mt") for i in range(n_envs)]
+    rnd = random.Random(widx)
+    q_out.put("ready")
+    while True:
+        cmd = q_in.get()
+        if cmd is None:
+            return
+        done_steps = 0
+        while done_steps < env_steps:
+            for e in envs:
+                _, _, d, _ = e.step(rnd.randrange(16))
+                if d:
+                    e.reset()
+            done_steps += n_envs
+        q_out.put(done_steps)
+
+
+class PythonReferencePool:
+    """SubprocVecEnv-style pool over the UNMODIFIED reference FutbolEnv: P processes x M envs each."""
+
+    def __init__(self, procs, envs_per_proc, env_steps_per_step):
+        import multiprocessing as mp
+        ctx = mp.get_context("fork")
+        self.procs, self.q_in, self.q_out = [], [], ctx.Queue()
+        for w in range(procs):
+            qi = ctx.Queue()
+            p = ctx.Process(target=_py_ref_worker, args=(w, envs_per_proc, env_steps_per_step, qi, self.q_out), daemon=True)
+            p.start()
+            self.procs.append(p); self.q_in.append(qi)
+        for _ in range(procs):
+            assert self.q_out.get(timeout=120) == "ready"
+
+    def step(self):
+        for qi in self.q_in:
+            qi.put(1)
+        return sum(self.q_out.get() for _ in self.procs)
+
+    def close(self):
+        for qi in self.q_in:
+            qi.put(None)
+        for p in self.procs:
+            p.join(timeout=5)
+
+
+def python_reference_available():
+    from oracle.ref_harness import find_reference_root
+    return find_reference_root()
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    base = {"metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "impl": "reference", "gpu_launches": 0,
+            "config": {"workload": "FutbolEnv v0 2v2 vs hard-coded opponents (random_opp=False), uniform random AI actions, "
+                                   "reset on done; bounded CPU sample of the 2^20-env x K=64 workload"}}
+    root = python_reference_available()
+    if root is not None:
+        per_proc_steps = 1500                     # env-steps per process per bench step (~0.15 s)
+        pool = PythonReferencePool(cores, 4, per_proc_steps)
+        for _ in range(args.warmup):
+            pool.step()
+        t0 = time.perf_counter()
+        total = sum(pool.step() for _ in range(args.steps))
+        dt = time.perf_counter() - t0
+        pool.close()
+        val = total / dt
+        kind = "reference"
+        sample = ("unmodified reference FutbolEnv (%s) with gym/matplotlib stand-ins and an injected stdlib-MT RNG; "
+                  "%d processes x 4 envs, %d env-steps per bench step" % (root, cores, total // max(1, args.steps)))
+    else:
+        port = cpu_port_baseline(budget_s=max(5.0, 1.0 * args.steps), threads=cores)
+        val, dt, kind, sample = port["value"], None, "port", port["sample"]
+    base.update({"value": val, "ms_per_step": (dt / args.steps * 1e3) if dt else None,
+                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base), flush=True)
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=TOTAL_ENVS, help="total envs of the job (default 2^20)")
+    ap.add_argument("--random-opp", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gym_futbol_b200 import FutbolVecEnv
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert args.envs % world == 0
+    n_local = args.envs // world
+    K = ROLLOUT_K
+    env = FutbolVecEnv(n_local, device=dev, seed=0, env_id_offset=rank * n_local, random_opp=bool(args.random_opp))
+    env.reset()
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    acts = torch.randint(0, 16, (K, n_local), dtype=torch.uint8, device=dev, generator=g)   # resident in HBM
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput (`value`) ----
+    for _ in range(max(3, args.warmup)):
+        env.rollout(K, actions=acts)
+    barrier()
+    launches0 = env.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for a, b in evs:
+        a.record(stream)
+        env.rollout(K, actions=acts)
+        b.record(stream)
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = env.launch_count - launches0
+    elapsed_ms = t_start.elapsed_time(t_end)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, kernel_ms = t.tolist()
+    value = args.envs * K * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (`e2e`) ----
+    h_acts = torch.randint(0, 16, (K, n_local), dtype=torch.uint8).pin_memory()
+    d_acts = torch.empty_like(acts)
+    h_rew = torch.empty((K, n_local), dtype=torch.float32).pin_memory()
+    h_done = torch.empty((K, n_local), dtype=torch.uint8).pin_memory()
+    h_stats = torch.empty(64, dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        d_acts.copy_(h_acts, non_blocking=True)
+        _, rew, done = env.rollout(K, actions=d_acts)
+        h_rew.copy_(rew, non_blocking=True)
+        h_done.copy_(done, non_blocking=True)
+        h_stats.copy_(env.stats, non_blocking=True)
+        stream.synchronize()                     # the host consumer needs this step's result before the next one
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = args.envs * K * e2e_steps / (t.item() * 1e-3)
+
+    stats = torch.from_numpy(env.stats.cpu().numpy().view("int64").copy()).to(dev)   # optional statistics gather
+    if world > 1:
+        dist.all_reduce(stats[1:6], op=dist.ReduceOp.SUM)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        achieved = n_local * K * BYTES_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "FutbolEnv v0 2v2 vs hard-coded opponents (random_opp=%s), %d envs total, fused K=%d "
+                                   "rollout per step, uniform random actions read from an HBM-resident [K,n] u8 tensor"
+                                   % (bool(args.random_opp), args.envs, K),
+                       "envs_per_gpu": n_local, "rollout_k": K, "parallelism": "env-sharded x%d, no collective" % world,
+                       "l2": "each step writes %.2f GB per GPU (obs/reward/done), larger than the 126 MB L2"
+                             % (n_local * K * 125 / 1e9)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_acts.numel()) * world,
+                    "d2h_bytes_per_step": int(h_rew.numel() * 4 + h_done.numel() + 64) * world,
+                    "note": "pinned-host actions in; reward, done and statistics out; observations stay in HBM for "
+                            "the policy (zero-copy) by design"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "v0_rollout_kernel",
+                         "bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": kernel_ms,
+                         "note": "instruction-issue bound (fp64 sqrt/div, divergent action branches), see profiles/"},
+            "rollout_stats": {"episodes": int(stats[2]), "goals_ai": int(stats[3]), "goals_opp": int(stats[4]),
+                              "out_of_field": int(stats[5])},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_port_baseline()
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

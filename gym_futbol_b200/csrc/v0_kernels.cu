@@ -1,0 +1,276 @@
+// v0 kernels: reset, per-step, fused K-step rollout, AoS<->SoA state access.
+//
+// HBM layout of the state buffer (structure of arrays, `np` = n_envs rounded up to 256 so every
+// section starts 256-byte aligned and every warp's accesses are fully coalesced):
+//   double  f[25][np]     rows ai_1, ai_2, opp_1, opp_2, ball x (x, y, tx, ty, speed)
+//   uint64  t_total[np]
+//   int32   ep_step[np], ai_score[np], opp_score[np]
+//   uint8   owner[np], last_owner[np], flags[np]
+// = 223 bytes per env.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/futbol_b200.h"
+#include "v0_step.cuh"
+#include "v0_kernels.h"
+
+namespace futbol {
+
+struct StateView {
+    double *f; uint64_t *t_total; int32_t *ep_step, *ai_score, *opp_score; uint8_t *owner, *last_owner, *flags;
+    size_t np;
+};
+
+__host__ __device__ inline size_t v0_padded(int n) { return ((size_t)n + 255) & ~(size_t)255; }
+
+size_t v0_state_bytes(int n_envs) { return v0_padded(n_envs) * (25 * 8 + 8 + 3 * 4 + 3); }
+
+__host__ __device__ inline StateView make_view(void *base, int n)
+{
+    StateView v;
+    v.np = v0_padded(n);
+    char *p = (char *)base;
+    v.f = (double *)p;            p += v.np * 25 * 8;
+    v.t_total = (uint64_t *)p;    p += v.np * 8;
+    v.ep_step = (int32_t *)p;     p += v.np * 4;
+    v.ai_score = (int32_t *)p;    p += v.np * 4;
+    v.opp_score = (int32_t *)p;   p += v.np * 4;
+    v.owner = (uint8_t *)p;       p += v.np;
+    v.last_owner = (uint8_t *)p;  p += v.np;
+    v.flags = (uint8_t *)p;
+    return v;
+}
+
+__device__ __forceinline__ void load_state(const StateView &v, int i, V0State &s)
+{
+    const double *f = v.f + i;
+    const size_t np = v.np;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        s.p[r].x = f[(r * 5 + 0) * np]; s.p[r].y = f[(r * 5 + 1) * np]; s.p[r].tx = f[(r * 5 + 2) * np];
+        s.p[r].ty = f[(r * 5 + 3) * np]; s.p[r].sp = f[(r * 5 + 4) * np];
+    }
+    s.b.x = f[20 * np]; s.b.y = f[21 * np]; s.b.tx = f[22 * np]; s.b.ty = f[23 * np]; s.b.sp = f[24 * np];
+    s.t_total = v.t_total[i];
+    s.ep_step = v.ep_step[i]; s.ai_score = v.ai_score[i]; s.opp_score = v.opp_score[i];
+    s.owner = v.owner[i]; s.last_owner = v.last_owner[i];
+}
+
+__device__ __forceinline__ void store_state(const StateView &v, int i, const V0State &s, int flags)
+{
+    double *f = v.f + i;
+    const size_t np = v.np;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        f[(r * 5 + 0) * np] = s.p[r].x; f[(r * 5 + 1) * np] = s.p[r].y; f[(r * 5 + 2) * np] = s.p[r].tx;
+        f[(r * 5 + 3) * np] = s.p[r].ty; f[(r * 5 + 4) * np] = s.p[r].sp;
+    }
+    f[20 * np] = s.b.x; f[21 * np] = s.b.y; f[22 * np] = s.b.tx; f[23 * np] = s.b.ty; f[24 * np] = s.b.sp;
+    v.t_total[i] = s.t_total;
+    v.ep_step[i] = s.ep_step; v.ai_score[i] = s.ai_score; v.opp_score[i] = s.opp_score;
+    v.owner[i] = (uint8_t)s.owner; v.last_owner[i] = (uint8_t)s.last_owner; v.flags[i] = (uint8_t)flags;
+}
+
+// ---- observation output ------------------------------------------------------------------------
+// A thread's observation is 30 consecutive values, so lane-strided stores would touch 30 cache lines
+// per instruction.  fp32 rows are therefore staged through shared memory per warp and written out as
+// consecutive 128-bit stores (a warp's 32 rows are one contiguous 3840-byte span of [n, 30]).
+constexpr int kObsDim = 30;
+
+__device__ __forceinline__ void warp_store_obs_f32(float *smem_warp, const V0State &s, float *gdst_warp_row0,
+                                                   int lane, int rows_in_warp, bool vec_ok)
+{
+    for_each_obs(s, [&](int k, double v) { smem_warp[lane * kObsDim + k] = (float)v; });
+    __syncwarp();
+    const int total = rows_in_warp * kObsDim;
+    if (vec_ok) {
+        const int nvec = total >> 2;
+        const float4 *src = reinterpret_cast<const float4 *>(smem_warp);
+        float4 *dst = reinterpret_cast<float4 *>(gdst_warp_row0);
+        for (int q = lane; q < nvec; q += 32) __stcs(dst + q, src[q]);
+        for (int q = (nvec << 2) + lane; q < total; q += 32) __stcs(gdst_warp_row0 + q, smem_warp[q]);
+    } else {
+        for (int q = lane; q < total; q += 32) __stcs(gdst_warp_row0 + q, smem_warp[q]);
+    }
+    __syncwarp();
+}
+
+template <typename T>
+__device__ __forceinline__ void thread_store_obs(T *dst_row, const V0State &s)
+{
+    for_each_obs(s, [&](int k, double v) { dst_row[k] = (T)v; });
+}
+
+// ---- reset ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) v0_reset_kernel(V0Params P, StateView v, const uint8_t *mask, T *obs, int init)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_envs) return;
+    if (mask != nullptr && mask[i] == 0) return;
+    V0State s;
+    s.t_total = init ? 0 : v.t_total[i];
+    reset_env(s);
+    store_state(v, i, s, 0);
+    if (obs != nullptr) thread_store_obs(obs + (size_t)i * kObsDim, s);
+}
+
+// ---- per-step API ----------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) v0_step_kernel(V0Params P, StateView v, const uint8_t *actions, T *obs,
+                                                      T *reward, uint8_t *done, T *final_obs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_envs) return;
+    V0State s;
+    load_state(v, i, s);
+    const StepResult r = v0_step(s, P, P.env_id_offset + (uint32_t)i, actions[i] & 15);
+    if (r.done && P.auto_reset) {
+        if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * kObsDim, s);
+        reset_env(s);
+    }
+    store_state(v, i, s, r.flags);
+    if (obs != nullptr) thread_store_obs(obs + (size_t)i * kObsDim, s);
+    if (reward != nullptr) reward[i] = (T)r.reward;
+    if (done != nullptr) done[i] = (uint8_t)r.done;
+}
+
+// ---- fused K-step rollout ----------------------------------------------------------------------------
+constexpr int kRolloutThreads = 128;
+
+__global__ void __launch_bounds__(kRolloutThreads)
+v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ actions, float *__restrict__ obs,
+                  float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
+{
+    __shared__ __align__(16) float stage[kRolloutThreads / 32][32 * kObsDim];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_env0 = i - lane;
+    if (warp_env0 >= P.n_envs) return;            // whole warp out of range
+    const bool live = i < P.n_envs;
+    const int rows_in_warp = min(32, P.n_envs - warp_env0);
+    const size_t n = (size_t)P.n_envs;
+    // 128-bit stores need every step's row block 16-byte aligned: n*30*4 % 16 == 0  <=>  n even
+    const bool vec_ok = ((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
+    const uint32_t env_id = P.env_id_offset + (uint32_t)i;
+
+    V0State s;
+    if (live) load_state(v, i, s);
+    else { s.t_total = 0; reset_env(s); }
+
+    double reward_sum = 0.0;
+    uint32_t episodes = 0, goals_ai = 0, goals_opp = 0, fixes = 0;
+    int last_flags = 0;
+
+    for (int k = 0; k < K; ++k) {
+        const size_t slot = (size_t)k * n + (size_t)i;
+        int a;
+        if (actions != nullptr) a = live ? (__ldg(actions + slot) & 15) : 0;
+        else a = philox_action(P.seed, env_id, s.t_total, 16);
+        const int ai_before = s.ai_score;
+        const StepResult r = v0_step(s, P, env_id, a);
+        last_flags = r.flags;
+        reward_sum += r.reward;
+        goals_ai += (r.flags & kFlagGoal) && s.ai_score != ai_before;
+        goals_opp += (r.flags & kFlagGoal) && s.ai_score == ai_before;
+        fixes += (r.flags & kFlagFix) != 0;
+        episodes += r.done;
+        if (r.done && P.auto_reset) reset_env(s);
+        if (obs != nullptr)
+            warp_store_obs_f32(stage[warp], s, obs + ((size_t)k * n + (size_t)warp_env0) * kObsDim, lane, rows_in_warp, vec_ok);
+        if (live) {
+            if (reward != nullptr) __stcs(reward + slot, (float)r.reward);
+            if (done != nullptr) done[slot] = (uint8_t)r.done;
+        }
+    }
+    if (live) store_state(v, i, s, last_flags);
+
+    if (stats != nullptr) {
+        if (!live) { reward_sum = 0.0; episodes = goals_ai = goals_opp = fixes = 0; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            reward_sum += __shfl_xor_sync(0xffffffffu, reward_sum, o);
+            episodes += __shfl_xor_sync(0xffffffffu, episodes, o);
+            goals_ai += __shfl_xor_sync(0xffffffffu, goals_ai, o);
+            goals_opp += __shfl_xor_sync(0xffffffffu, goals_opp, o);
+            fixes += __shfl_xor_sync(0xffffffffu, fixes, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&stats->reward_sum, reward_sum);
+            atomicAdd((unsigned long long *)&stats->env_steps, (unsigned long long)rows_in_warp * (unsigned long long)K);
+            atomicAdd((unsigned long long *)&stats->episodes, (unsigned long long)episodes);
+            atomicAdd((unsigned long long *)&stats->goals_ai, (unsigned long long)goals_ai);
+            atomicAdd((unsigned long long *)&stats->goals_opp, (unsigned long long)goals_opp);
+            atomicAdd((unsigned long long *)&stats->out_of_field, (unsigned long long)fixes);
+        }
+    }
+}
+
+// ---- AoS <-> SoA -------------------------------------------------------------------------------------
+__global__ void v0_get_state_kernel(int n, StateView v, FutbolV0EnvState *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    FutbolV0EnvState e;
+    for (int k = 0; k < 25; ++k) e.rows[k / 5][k % 5] = v.f[(size_t)k * v.np + i];
+    e.t_total = v.t_total[i]; e.ep_step = v.ep_step[i]; e.ai_score = v.ai_score[i]; e.opp_score = v.opp_score[i];
+    e.owner = v.owner[i]; e.last_owner = v.last_owner[i]; e.flags = v.flags[i]; e.pad_ = 0;
+    out[i] = e;
+}
+
+__global__ void v0_set_state_kernel(int n, StateView v, const FutbolV0EnvState *in)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const FutbolV0EnvState e = in[i];
+    for (int k = 0; k < 25; ++k) v.f[(size_t)k * v.np + i] = e.rows[k / 5][k % 5];
+    v.t_total[i] = e.t_total; v.ep_step[i] = e.ep_step; v.ai_score[i] = e.ai_score; v.opp_score[i] = e.opp_score;
+    v.owner[i] = e.owner; v.last_owner[i] = e.last_owner; v.flags[i] = e.flags;
+}
+
+// ---- host launchers ------------------------------------------------------------------------------------
+static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
+
+cudaError_t v0_launch_reset(const V0Params &P, void *state, const uint8_t *mask, void *obs, int obs_f64, int init,
+                            cudaStream_t st)
+{
+    const StateView v = make_view(state, P.n_envs);
+    if (obs_f64) v0_reset_kernel<double><<<blocks_for(P.n_envs, 128), 128, 0, st>>>(P, v, mask, (double *)obs, init);
+    else v0_reset_kernel<float><<<blocks_for(P.n_envs, 128), 128, 0, st>>>(P, v, mask, (float *)obs, init);
+    return cudaGetLastError();
+}
+
+cudaError_t v0_launch_step(const V0Params &P, void *state, const uint8_t *actions, void *obs, void *reward,
+                           uint8_t *done, void *final_obs, int out_f64, cudaStream_t st)
+{
+    const StateView v = make_view(state, P.n_envs);
+    if (out_f64)
+        v0_step_kernel<double><<<blocks_for(P.n_envs, 128), 128, 0, st>>>(P, v, actions, (double *)obs, (double *)reward,
+                                                                          done, (double *)final_obs);
+    else
+        v0_step_kernel<float><<<blocks_for(P.n_envs, 128), 128, 0, st>>>(P, v, actions, (float *)obs, (float *)reward,
+                                                                         done, (float *)final_obs);
+    return cudaGetLastError();
+}
+
+cudaError_t v0_launch_rollout(const V0Params &P, void *state, int K, const uint8_t *actions, float *obs, float *reward,
+                              uint8_t *done, FutbolStats *stats, cudaStream_t st)
+{
+    const StateView v = make_view(state, P.n_envs);
+    v0_rollout_kernel<<<blocks_for(P.n_envs, kRolloutThreads), kRolloutThreads, 0, st>>>(P, v, K, actions, obs, reward,
+                                                                                         done, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t v0_launch_get_state(int n, const void *state, void *aos, cudaStream_t st)
+{
+    v0_get_state_kernel<<<blocks_for(n, 128), 128, 0, st>>>(n, make_view(const_cast<void *>(state), n), (FutbolV0EnvState *)aos);
+    return cudaGetLastError();
+}
+
+cudaError_t v0_launch_set_state(int n, void *state, const void *aos, cudaStream_t st)
+{
+    v0_set_state_kernel<<<blocks_for(n, 128), 128, 0, st>>>(n, make_view(state, n), (const FutbolV0EnvState *)aos);
+    return cudaGetLastError();
+}
+
+}  // namespace futbol

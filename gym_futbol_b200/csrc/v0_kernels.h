@@ -1,0 +1,18 @@
+// Host-side launchers of the v0 kernels (defined in v0_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/futbol_b200.h"
+#include "v0_step.cuh"
+
+namespace futbol {
+size_t v0_state_bytes(int n_envs);
+cudaError_t v0_launch_reset(const V0Params &P, void *state, const uint8_t *mask, void *obs, int obs_f64, int init,
+                            cudaStream_t st);
+cudaError_t v0_launch_step(const V0Params &P, void *state, const uint8_t *actions, void *obs, void *reward,
+                           uint8_t *done, void *final_obs, int out_f64, cudaStream_t st);
+cudaError_t v0_launch_rollout(const V0Params &P, void *state, int K, const uint8_t *actions, float *obs, float *reward,
+                              uint8_t *done, FutbolStats *stats, cudaStream_t st);
+cudaError_t v0_launch_get_state(int n, const void *state, void *aos, cudaStream_t st);
+cudaError_t v0_launch_set_state(int n, void *state, const void *aos, cudaStream_t st);
+}  // namespace futbol

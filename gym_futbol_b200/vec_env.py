@@ -1,0 +1,154 @@
+"""Batched front end: n environments stepped by one CUDA launch, tensors stay on the device.
+
+Mirrors the call surface stable-baselines' ``DummyVecEnv`` gives the reference's training loop
+(colab_notebook.ipynb:818-823): ``reset() -> obs[n, ...]``, ``step(actions[n]) -> (obs, rewards,
+dones, infos)`` with auto-reset on done and the terminal observation exposed separately, plus
+``rollout(K)``: the caller's ``for t: step(a_t)`` loop fused into one launch.
+
+All returned tensors are views of persistent device buffers owned by this object (zero-copy for
+the policy); they are overwritten by the next ``step`` / ``rollout`` call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, spaces
+
+OBS_DIM_V0 = 30
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class FutbolVecEnv:
+    """v0 ``FutbolEnv`` (gym_futbol/envs/futbol_env.py) x ``num_envs`` on one GPU."""
+
+    def __init__(self, num_envs, device="cuda:0", seed=0, env_id_offset=0, random_opp=True, one_goal_end=False,
+                 only_reward_goal=False, game_time=40, player_speed=12, shoot_speed=20, auto_reset=True,
+                 dtype=torch.float32):
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("dtype must be torch.float32 or torch.float64")
+        if int(num_envs) <= 0:
+            raise ValueError("num_envs must be positive")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise _lib.FutbolError("FutbolVecEnv needs a CUDA device; there is no CPU fallback")
+        self.num_envs = int(num_envs)
+        self.dtype = dtype
+        self._dt = 1 if dtype == torch.float64 else 0
+        self.cfg = _lib.FutbolConfig(_lib.ABI_VERSION, _lib.VARIANT_V0, self.num_envs, int(env_id_offset), int(seed), 2,
+                                     int(bool(random_opp)), int(bool(one_goal_end)), int(bool(only_reward_goal)),
+                                     int(bool(auto_reset)), int(shoot_speed), float(game_time), float(player_speed))
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.futbol_create(C.byref(self.cfg), C.byref(h)))
+        self._h = h
+        n = self.num_envs
+        self.state = torch.zeros(self.lib.futbol_state_bytes(h), dtype=torch.uint8, device=self.device)
+        self.obs = torch.zeros((n, OBS_DIM_V0), dtype=dtype, device=self.device)
+        self.rewards = torch.zeros(n, dtype=dtype, device=self.device)
+        self.dones = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        self.final_obs = torch.zeros((n, OBS_DIM_V0), dtype=dtype, device=self.device)
+        self.stats = torch.zeros(_lib.STATS_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+        self._roll = {}
+        self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(OBS_DIM_V0,), dtype=np.float32)
+        self.action_space = spaces.Discrete(16)
+        self.episode_steps = self.lib.futbol_draw_limit_steps(h)
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.futbol_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self.lib.futbol_launch_count(self._h))
+
+    def _actions(self, actions, shape):
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions), device=self.device)
+        if tuple(actions.shape) != shape:
+            raise ValueError("actions must have shape %s, got %s" % (shape, tuple(actions.shape)))
+        if actions.device != self.device:
+            actions = actions.to(self.device, non_blocking=True)
+        if actions.dtype != torch.uint8:
+            actions = actions.to(torch.uint8)
+        return actions.contiguous()
+
+    # ------------------------------------------------------------------ gym-style API
+    def reset(self, mask=None):
+        """Reset all envs (or those with mask != 0); returns obs [n, 30]."""
+        with torch.cuda.device(self.device):
+            m = None if mask is None else self._actions(mask, (self.num_envs,))
+            _lib.check(self.lib.futbol_reset(self._h, _ptr(self.state), _ptr(m), _ptr(self.obs), self._dt, self._stream()))
+        return self.obs
+
+    def step(self, actions):
+        """actions: [n] ints in 0..15 (ai_1 = a // 4, ai_2 = a % 4)."""
+        with torch.cuda.device(self.device):
+            a = self._actions(actions, (self.num_envs,))
+            _lib.check(self.lib.futbol_step(self._h, _ptr(self.state), _ptr(a), _ptr(self.obs), _ptr(self.rewards),
+                                            _ptr(self.dones), _ptr(self.final_obs), self._dt, self._stream()))
+        return self.obs, self.rewards, self.dones, {"terminal_observation": self.final_obs}
+
+    def rollout(self, K, actions=None, obs=True, reward=True, done=True):
+        """K fused steps.  actions: uint8 [K, n] or None (uniform random actions drawn in-kernel).
+
+        Returns (obs [K, n, 30] f32, reward [K, n] f32, done [K, n] u8); buffers are cached per K.
+        """
+        K = int(K)
+        n = self.num_envs
+        buf = self._roll.get(K)
+        if buf is None:
+            buf = (torch.empty((K, n, OBS_DIM_V0), dtype=torch.float32, device=self.device),
+                   torch.empty((K, n), dtype=torch.float32, device=self.device),
+                   torch.empty((K, n), dtype=torch.uint8, device=self.device))
+            self._roll[K] = buf
+        o, r, d = buf
+        with torch.cuda.device(self.device):
+            a = None if actions is None else self._actions(actions, (K, n))
+            _lib.check(self.lib.futbol_rollout(self._h, _ptr(self.state), K, _ptr(a), _ptr(o if obs else None),
+                                               _ptr(r if reward else None), _ptr(d if done else None),
+                                               _ptr(self.stats), self._stream()))
+        return (o if obs else None), (r if reward else None), (d if done else None)
+
+    # ------------------------------------------------------------------ state / statistics
+    def get_state(self):
+        """Complete env state as a numpy structured array (``_lib.V0_ENV_STATE``); synchronises."""
+        aos = torch.empty(self.num_envs * _lib.V0_ENV_STATE.itemsize, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.futbol_get_state(self._h, _ptr(self.state), _ptr(aos), self._stream()))
+        return aos.cpu().numpy().view(_lib.V0_ENV_STATE).copy()
+
+    def set_state(self, records):
+        records = np.ascontiguousarray(records, dtype=_lib.V0_ENV_STATE)
+        if records.shape != (self.num_envs,):
+            raise ValueError("need %d state records" % self.num_envs)
+        aos = torch.from_numpy(records.view(np.uint8).copy()).to(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.futbol_set_state(self._h, _ptr(self.state), _ptr(aos), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def read_stats(self, clear=False):
+        """Accumulated rollout statistics (sums over envs and steps); synchronises."""
+        rec = self.stats.cpu().numpy().view(_lib.STATS_DTYPE)[0]
+        out = {k: (float(rec[k]) if k == "reward_sum" else int(rec[k])) for k in
+               ("reward_sum", "env_steps", "episodes", "goals_ai", "goals_opp", "out_of_field")}
+        if clear:
+            self.stats.zero_()
+        return out

@@ -1,0 +1,125 @@
+/*
+ * futbol_b200 -- C ABI of the B200-native batched gym-futbol environment step.
+ *
+ * This is the drop-in boundary for ONE hot path of yc2454/gym-futbol: the environment
+ * step (reference: gym_futbol/envs/futbol_env.py FutbolEnv.reset :205-245 / .step :628-717
+ * and gym_futbol/envs_v1/futbol_env.py Futbol.reset :145-150 / .step :427-483).  The
+ * reference has no native interface (it is pure Python; v1 calls Chipmunk2D through
+ * pymunk/cffi), so every entry point below names the Python method it replaces.  The
+ * reference-side binding a maintainer would add is the ctypes stub in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every data pointer is a DEVICE pointer owned by the caller
+ *     (e.g. a torch CUDA tensor's data_ptr()); `stream` is a cudaStream_t passed as void*.
+ *   - all work is enqueued on `stream`; no call synchronises the host.
+ *   - return value: 0 = ok, <0 = error (see futbol_last_error()); nothing throws.
+ *   - one handle per (process, device); calls on a handle are serialised by the caller.
+ *   - the library allocates nothing persistent on the device except a 64-byte statistics
+ *     scratch inside the handle.
+ */
+#ifndef FUTBOL_B200_H
+#define FUTBOL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FUTBOL_ABI_VERSION 1
+
+enum { FUTBOL_VARIANT_V0 = 0, /* FutbolEnv: 2v2 kinematic, possession state machine */
+       FUTBOL_VARIANT_V1 = 1  /* Futbol: NvN, circle/segment rigid-body physics     */ };
+
+enum { FUTBOL_OK = 0, FUTBOL_ERR_ARG = -1, FUTBOL_ERR_CUDA = -2, FUTBOL_ERR_UNSUPPORTED = -3 };
+
+/* Constructor arguments of the reference classes (v0: futbol_env.py:134-138,
+ * v1: envs_v1/futbol_env.py:63-65) plus what batching adds. */
+typedef struct FutbolConfig {
+    int32_t  abi_version;      /* FUTBOL_ABI_VERSION */
+    int32_t  variant;          /* FUTBOL_VARIANT_* */
+    int32_t  n_envs;           /* envs held by this handle (this device's shard) */
+    uint32_t env_id_offset;    /* global id of local env 0: RNG is keyed by global id, so
+                                  trajectories do not depend on how envs are sharded */
+    uint64_t seed;
+    int32_t  n_players;        /* players per team: v0 must be 2; v1 1..10 (number_of_player) */
+    int32_t  random_opp;       /* v0 random_opp (:138) */
+    int32_t  one_goal_end;     /* v0 one_goal_end (:137) */
+    int32_t  only_reward_goal; /* v0 only_reward_goal (:137) */
+    int32_t  auto_reset;       /* 1: VecEnv semantics -- an env that returns done is reset in the
+                                  same call and its obs slot holds the reset observation */
+    int32_t  shoot_speed;      /* v0 shoot_speed (:136), default 20 */
+    double   game_time;        /* v0 game_time (:135) = 40; v1 total_time (:63) = 30 */
+    double   player_speed;     /* v0 player_speed (:135) = 12 */
+} FutbolConfig;
+
+typedef struct FutbolHandle FutbolHandle;
+
+/* One env's complete v0 state in array-of-structs form, for get/set_state (checkpoint,
+ * parity tests).  In HBM the state is structure-of-arrays; see DESIGN.md. */
+typedef struct FutbolV0EnvState {
+    double   rows[5][5];   /* ai_1, ai_2, opp_1, opp_2, ball: x, y, tx, ty, speed (obs rows 0-4) */
+    uint64_t t_total;      /* steps since creation = Philox step index (not cleared by reset) */
+    int32_t  ep_step;      /* steps since the last reset (reference `time` = ep_step additions of 0.1) */
+    int32_t  ai_score, opp_score;
+    uint8_t  owner, last_owner;  /* BallOwner 0..4 (ballowner.py:3-7) */
+    uint8_t  flags;        /* of the last step: 1 goal, 2 out-of-field fix, 4 done */
+    uint8_t  pad_;
+} FutbolV0EnvState;
+
+/* Rollout statistics (sums over all envs and steps of one futbol_rollout call). */
+typedef struct FutbolStats {
+    double   reward_sum;
+    uint64_t env_steps, episodes, goals_ai, goals_opp, out_of_field;
+    uint64_t reserved[2];
+} FutbolStats;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+/* replaces FutbolEnv.__init__ (futbol_env.py:134-201) / Futbol.__init__ (envs_v1:63-127) */
+int futbol_create(const FutbolConfig *cfg, FutbolHandle **out);
+int futbol_destroy(FutbolHandle *h);
+const char *futbol_last_error(void);
+int futbol_abi_version(void);
+
+/* ---- sizes ------------------------------------------------------------------------- */
+size_t futbol_state_bytes(const FutbolHandle *h); /* bytes of the opaque SoA state buffer */
+int futbol_obs_dim(const FutbolHandle *h);        /* v0: 30 (=6x5); v1: 4 + 8*n_players */
+int futbol_act_dim(const FutbolHandle *h);        /* v0: 1 (Discrete(16)); v1: 2*n_players */
+int futbol_draw_limit_steps(const FutbolHandle *h); /* v0: episode length in steps (401 at game_time 40) */
+
+/* ---- reset: FutbolEnv.reset (futbol_env.py:205-245) / Futbol.reset (envs_v1:145-150) --
+ * mask: NULL = all envs, else uint8[n_envs], non-zero = reset that env.
+ * obs: NULL or [n_envs, obs_dim] in `obs_dtype` (0 = float32, 1 = float64). */
+int futbol_reset(FutbolHandle *h, void *state, const uint8_t *mask, void *obs, int obs_dtype, void *stream);
+
+/* ---- step: FutbolEnv.step (futbol_env.py:628-717) / Futbol.step (envs_v1:427-483) -----
+ * actions: v0 uint8[n_envs] in 0..15 (ai_1 = a/4, ai_2 = a%4, :653);
+ *          v1 uint8[n_envs, 2*n_players] (arrow, key) per left-team player.
+ * obs: [n_envs, obs_dim]; reward: [n_envs]; both in `out_dtype` (0 = float32, 1 = float64).
+ * done: uint8[n_envs].  final_obs: NULL or [n_envs, obs_dim]: with auto_reset, the terminal
+ * observation of envs that finished in this call (other rows untouched). */
+int futbol_step(FutbolHandle *h, void *state, const uint8_t *actions, void *obs, void *reward,
+                uint8_t *done, void *final_obs, int out_dtype, void *stream);
+
+/* ---- fused K-step rollout: the caller's `for t: env.step(a_t)` loop in one launch ------
+ * State stays in registers across the K steps.  actions: uint8 [K, n_envs(, act_dim)] or NULL
+ * (NULL = uniform random actions generated in-kernel from Philox stream 1 = synthetic load).
+ * obs: float32 [K, n_envs, obs_dim]; reward: float32 [K, n_envs]; done: uint8 [K, n_envs];
+ * any of the three may be NULL (not written).  stats: NULL or a device FutbolStats that the
+ * call ACCUMULATES into.  auto_reset semantics as futbol_step. */
+int futbol_rollout(FutbolHandle *h, void *state, int K, const uint8_t *actions, float *obs,
+                   float *reward, uint8_t *done, FutbolStats *stats, void *stream);
+
+/* ---- state access (device AoS records, FutbolV0EnvState for v0) --------------------- */
+size_t futbol_env_state_bytes(const FutbolHandle *h); /* sizeof one AoS record */
+int futbol_get_state(FutbolHandle *h, const void *state, void *aos_out, void *stream);
+int futbol_set_state(FutbolHandle *h, void *state, const void *aos_in, void *stream);
+
+/* number of kernels this handle has launched (bench.py's gpu_launches) */
+uint64_t futbol_launch_count(const FutbolHandle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUTBOL_B200_H */

@@ -18,10 +18,20 @@
  * Randomness: the reference uses unseeded global generators; parity is defined on the
  * injected Philox4x32-10 stream specified in oracle/philox.py (same maps here).
  *
- * Arithmetic note: numpy-scalar ``x**2`` (futbol_env.py:64,562; easy_agent.py:12) is
- * libm ``pow(x, 2.0)``, which is not always equal to ``x*x``.  ``sq_mode`` selects:
- *   1 = pow(x,2.0)  (bit-identical to the Python reference on the same glibc; default)
- *   0 = x*x         (what the CUDA kernel computes)
+ * Arithmetic modes (``arith``).  The reference's floats depend on the host libm in two places:
+ * numpy-scalar ``x**2`` (futbol_env.py:64,562; easy_agent.py:12) is libm ``pow(x, 2.0)``, which is
+ * not correctly rounded (differs from x*x for ~0.09 % of inputs), and math.sin/cos/log
+ * (:108-110, Box-Muller in the injected normal()).  No GPU can reproduce glibc's last-bit choices,
+ * and the game has structural knife edges (e.g. an opponent chasing its own shot closes on the ball
+ * by exactly 0.1 per step and is then tested with ``distance <= 1``), so last-bit differences do
+ * flip integer outcomes now and then.  Therefore two modes:
+ *   arith = 1 "libm":   pow(x,2.0) + libm sin/cos/log -- bit-identical to the Python reference on
+ *                       the same glibc; this is the mode the golden vectors pin.
+ *   arith = 0 "kernel": x*x + the fully specified fm_log / fm_sincos below (fdlibm-style polynomials,
+ *                       only IEEE add/mul/div, no FMA) -- the arithmetic the CUDA kernel implements, so
+ *                       kernel and oracle can be compared BIT-exactly at any scale.
+ * tests/test_oracle_v0.py quantifies libm-vs-kernel mode: identical integers except where a compare was
+ * decided by a last-bit difference, floats ~1e-13 otherwise.
  *
  * Build: see oracle/Makefile  (gcc -O2 -ffp-contract=off -fno-builtin-pow -shared -fPIC).
  */
@@ -59,7 +69,7 @@ typedef struct {
     int32_t random_opp;       /* futbol_env.py:138 */
     int32_t one_goal_end;     /* :137 */
     int32_t only_reward_goal; /* :137 */
-    int32_t sq_mode;          /* 1 = pow(x,2.0), 0 = x*x */
+    int32_t arith;            /* 1 = libm (pow, sin, cos, log), 0 = kernel arithmetic (x*x, fm_*) */
     int32_t rng_const;        /* 1 = constant RNG of SURVEY.md Appendix A (randint->a, random->0.5,
                                  uniform->(a+b)/2, normal->0); draws are still counted */
     int32_t pad_;
@@ -72,8 +82,10 @@ typedef struct {
     double obs[6][5];    /* rows ai_1, ai_2, opp_1, opp_2, ball, owner one-hot*10 */
     double kick[4][2];   /* frozen kickoff views of the four Easy_Agents (Q1) */
     double time;         /* float accumulator, :239,:716 */
-    uint64_t draw_ctr;   /* Philox stream-0 sequential draw counter */
-    uint64_t t_total;    /* total steps taken (action stream index) */
+    uint64_t draw_ctr;   /* draws consumed since construction (bookkeeping only) */
+    uint64_t t_total;    /* total steps taken = Philox step index; not cleared by reset */
+    uint32_t step_draws; /* draws consumed inside the current step (index j of the next draw) */
+    uint32_t pad_;
     uint32_t env_id;     /* global env id */
     int32_t owner, last_owner;
     int32_t ai_score, opp_score;
@@ -100,19 +112,87 @@ void futbol_oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t
     philox4x32_10(ctr, key, out);
 }
 
+/* ---- "kernel arithmetic": fully specified elementary functions ----------------------------------
+ * Domain needed: log on (0, 1] (Box-Muller), sin/cos on |x| <= 2*pi (Box-Muller angle and the kick
+ * swing angle, bounded by 5.77 sigma <= 289 degrees).  fdlibm-style kernels (e_log.c, k_sin.c, k_cos.c
+ * polynomials; two-term Cody-Waite reduction by pi/2), every operation an individually rounded IEEE
+ * double op in exactly this order.  Max error vs libm: 1 ulp (log), 2.3e-16 abs (sin/cos). */
+static double fm_log(double x)
+{
+    static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+        Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+        Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+        Lg7 = 1.479819860511658591e-01;
+    uint64_t b;
+    memcpy(&b, &x, 8);
+    int k = (int)((b >> 52) & 0x7ff) - 1023;
+    b = (b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
+    double m;
+    memcpy(&m, &b, 8);
+    if (m > 1.4142135623730951) { m = m * 0.5; k += 1; }
+    double f = m - 1.0;
+    double s = f / (2.0 + f);
+    double z = s * s, w = z * z;
+    double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+    double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    double R = t2 + t1;
+    double hfsq = (0.5 * f) * f;
+    double dk = (double)k;
+    return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+}
+static double fm_ksin(double x)
+{
+    static const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+        S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08,
+        S6 = 1.58969099521155010221e-10;
+    double z = x * x, v = z * x;
+    double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+    return x + v * (S1 + z * r);
+}
+static double fm_kcos(double x)
+{
+    static const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+        C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09,
+        C6 = -1.13596475577881948265e-11;
+    double z = x * x;
+    double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+    return (1.0 - 0.5 * z) + z * r;
+}
+static void fm_sincos(double x, double *s, double *c)
+{
+    static const double invpio2 = 6.36619772367581382433e-01, pio2_1 = 1.57079632673412561417e+00,
+        pio2_1t = 6.07710050650619224932e-11;
+    double fn = rint(x * invpio2);
+    int n = (int)fn;
+    double r = (x - fn * pio2_1) - fn * pio2_1t;
+    double sr = fm_ksin(r), cr = fm_kcos(r);
+    switch (n & 3) {
+    case 0: *s = sr; *c = cr; break;
+    case 1: *s = cr; *c = -sr; break;
+    case 2: *s = -sr; *c = -cr; break;
+    default: *s = -cr; *c = sr; break;
+    }
+}
+void futbol_oracle_fm(double x, double out[3]) { out[0] = x > 0 ? fm_log(x) : 0.0; fm_sincos(x, &out[1], &out[2]); }
+
 typedef struct { const OracleV0Config *cfg; OracleV0Env *e; } Ctx;
 
-static uint32_t draw_word(uint64_t seed, uint32_t env_id, uint32_t stream, uint64_t d)
+/* word j (per-step draw index) of step t -- counter layout: oracle/philox.py */
+static uint32_t draw_word(uint64_t seed, uint32_t env_id, uint32_t stream, uint64_t t, uint32_t j)
 {
-    uint64_t blk = d >> 2;
-    uint32_t ctr[4] = { (uint32_t)blk, (uint32_t)(blk >> 32), env_id, stream };
+    uint32_t blk = j >> 2;
+    uint32_t ctr[4] = { (uint32_t)t, ((uint32_t)(t >> 32) & 0xFFFFu) | (blk << 16), env_id, stream };
     uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
     uint32_t out[4];
     philox4x32_10(ctr, key, out);
-    return out[d & 3];
+    return out[j & 3];
 }
 
-static uint32_t next_u32(Ctx *c) { return draw_word(c->cfg->seed, c->e->env_id, 0, c->e->draw_ctr++); }
+static uint32_t next_u32(Ctx *c)
+{
+    c->e->draw_ctr++;
+    return draw_word(c->cfg->seed, c->e->env_id, 0, c->e->t_total, c->e->step_draws++);
+}
 static double rng_random(Ctx *c)
 {
     uint32_t w = next_u32(c);
@@ -130,18 +210,25 @@ static double rng_uniform(Ctx *c, double a, double b)
 }
 static void rng_normal10(Ctx *c, double mu, double sd, double out[10])
 {
-    if (c->cfg->rng_const) { c->e->draw_ctr += 20; for (int j = 0; j < 10; ++j) out[j] = 0.0; return; }
+    if (c->cfg->rng_const) { c->e->draw_ctr += 20; c->e->step_draws += 20; for (int j = 0; j < 10; ++j) out[j] = 0.0; return; }
     for (int j = 0; j < 10; ++j) {
         double u1 = (double)((next_u32(c) >> 8) + 1u) * (1.0 / 16777216.0);
         double u2 = (double)(next_u32(c) >> 8) * (1.0 / 16777216.0);
-        double z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+        double z;
+        if (c->cfg->arith) {
+            z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+        } else {
+            double sn, cs;
+            fm_sincos(6.283185307179586 * u2, &sn, &cs);
+            z = sqrt(-2.0 * fm_log(u1)) * cs;
+        }
         out[j] = mu + sd * z;
     }
 }
 
 int futbol_oracle_action(uint64_t seed, uint32_t env_id, uint64_t t, int n_actions)
 {
-    uint32_t ctr[4] = { (uint32_t)t, (uint32_t)(t >> 32), env_id, 1u };
+    uint32_t ctr[4] = { (uint32_t)t, (uint32_t)(t >> 32) & 0xFFFFu, env_id, 1u };
     uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
     uint32_t out[4];
     philox4x32_10(ctr, key, out);
@@ -151,7 +238,7 @@ int futbol_oracle_action(uint64_t seed, uint32_t env_id, uint64_t t, int n_actio
 /* ---- helpers: futbol_env.py:62-129 -------------------------------------------------- */
 /* gcc folds pow(x, 2.0) into x*x; the volatile pointer (and -fno-builtin-pow) keeps the libm call */
 static double (*volatile libm_pow)(double, double) = pow;
-static double sq(const Ctx *c, double x) { return c->cfg->sq_mode ? libm_pow(x, 2.0) : x * x; }
+static double sq(const Ctx *c, double x) { return c->cfg->arith ? libm_pow(x, 2.0) : x * x; }
 double futbol_oracle_libm_sq(double x) { return libm_pow(x, 2.0); }
 
 /* get_vec, :62-65 (duplicate easy_agent.py:10-13) */
@@ -182,7 +269,9 @@ static void screw_vec(Ctx *c, const double vec[2], double mag, double accuracy, 
     double sn = vec[1] * 1.0 / mag;                     /* :106 */
     int seed = rng_randint(c, 0, 9);                    /* :107 */
     double swing = (nd[seed] / 180) * 3.141592653589793; /* :108 */
-    double ssin = sin(swing), scos = cos(swing);        /* :109-110 */
+    double ssin, scos;                                  /* :109-110 */
+    if (c->cfg->arith) { ssin = sin(swing); scos = cos(swing); }
+    else fm_sincos(swing, &ssin, &scos);
     double tcos = (cs * scos) - (sn * ssin);            /* :113 */
     double tsin = (sn * scos) + (cs * ssin);            /* :114 */
     out[0] = tcos * mag;                                /* :115 */
@@ -537,6 +626,7 @@ int futbol_v0_oracle_step(const OracleV0Config *cfg, OracleV0Env *e, int ai_acti
     memcpy(o_ai_2, e->obs[AI_2], sizeof(o_ai_2));
     memcpy(o_owner, e->obs[OWNER_ROW], sizeof(o_owner));
     e->flags = 0;
+    e->step_draws = 0;
 
     if (cfg->random_opp) {                                  /* :639-645 */
         int r = rng_randint(c, 0, 15);

@@ -21,12 +21,17 @@ Philox4x32-10 (Salmon et al., SC'11), multipliers 0xD2511F53 / 0xCD9E8D57,
 Weyl constants 0x9E3779B9 / 0xBB67AE85.
 
   key      = (seed & 0xffffffff, seed >> 32)
-  counter  = (block & 0xffffffff, block >> 32, global_env_id, stream)
+  counter  = (t & 0xffffffff, ((t >> 32) & 0xffff) | (block << 16), global_env_id, stream)
 
-Streams: 0 = environment dynamics draws (sequential per-env draw counter ``d``;
-draw ``d`` is word ``d & 3`` of block ``d >> 2``); 1 = synthetic AI actions
-(block = total step index ``t`` of that env, word 0); 2 = v1 opponent actions
-and 3 = v1 dynamics draws (same sequential scheme as stream 0).
+``t`` is the env's total step index (number of ``step`` calls since creation; it is NOT
+cleared by ``reset``), ``block`` a 16-bit block index inside that step.  A step's
+randomness therefore depends only on (seed, env id, t): no RNG state is carried.
+
+Streams: 0 = environment dynamics draws.  The reference consumes a variable number of
+draws per step in a state-dependent order (SURVEY.md "RNG ledger"); draw ``j`` (0-based,
+in the reference's call order, restarting at 0 every step) is word ``j & 3`` of block
+``j >> 2``.  1 = synthetic AI actions (block 0, word 0).  2 = v1 opponent actions,
+3 = v1 dynamics draws (same per-step sequential scheme as stream 0).
 
 Draw -> value maps (``w`` = one 32-bit draw):
 
@@ -105,9 +110,13 @@ def u32_to_randint(w: int, a: int, b: int) -> int:
     return a + ((w * (b - a + 1)) >> 32)
 
 
+def step_counter(t: int, block: int, env_id: int, stream: int):
+    return (t & MASK, ((t >> 32) & 0xFFFF) | ((block & 0xFFFF) << 16), env_id & MASK, stream)
+
+
 def action_for(seed: int, env_id: int, t: int, n_actions: int = 16) -> int:
     """Synthetic AI action of global env ``env_id`` at its total step ``t``."""
-    w = philox4x32_10((t & MASK, (t >> 32) & MASK, env_id, STREAM_ACTIONS), seed_key(seed))[0]
+    w = philox4x32_10(step_counter(t, 0, env_id, STREAM_ACTIONS), seed_key(seed))[0]
     return (w * n_actions) >> 32
 
 
@@ -116,35 +125,47 @@ def actions_table(seed: int, env_ids, t0: int, steps: int, n_actions: int = 16) 
     env_ids = np.asarray(env_ids, dtype=np.uint64)
     t = np.arange(t0, t0 + steps, dtype=np.uint64)[:, None]
     k0, k1 = seed_key(seed)
-    w, _, _, _ = philox4x32_10_np(t & np.uint64(MASK), t >> np.uint64(32), env_ids[None, :],
+    w, _, _, _ = philox4x32_10_np(t & np.uint64(MASK), (t >> np.uint64(32)) & np.uint64(0xFFFF), env_ids[None, :],
                                   np.uint64(STREAM_ACTIONS), k0, k1)
     return ((w * np.uint64(n_actions)) >> np.uint64(32)).astype(np.uint8)
 
 
 class DrawStream:
-    """Sequential draw stream of one env (stream 0 or 3)."""
+    """Per-step sequential draw stream of one env (stream 0 or 3).
 
-    __slots__ = ("key", "env_id", "stream", "ctr", "_blk_idx", "_blk", "log")
+    The harness calls ``begin_step(t)`` before every ``env.step``; ``ctr`` is the number of
+    draws consumed so far inside the current step, ``total`` since construction.
+    """
 
-    def __init__(self, seed: int, env_id: int, stream: int = STREAM_DYNAMICS, ctr: int = 0):
+    __slots__ = ("key", "env_id", "stream", "t", "ctr", "total", "_blk_idx", "_blk", "log")
+
+    def __init__(self, seed: int, env_id: int, stream: int = STREAM_DYNAMICS):
         self.key = seed_key(seed)
         self.env_id = int(env_id)
         self.stream = stream
-        self.ctr = int(ctr)
-        self._blk_idx = -1
+        self.t = 0
+        self.ctr = 0
+        self.total = 0
+        self._blk_idx = None
         self._blk = None
         self.log = None  # set to a list to record (kind, value) per call
 
-    def word_at(self, d: int) -> int:
-        b = d >> 2
+    def begin_step(self, t: int):
+        self.t = int(t)
+        self.ctr = 0
+        self._blk_idx = None
+
+    def word_at(self, j: int) -> int:
+        b = j >> 2
         if b != self._blk_idx:
-            self._blk = philox4x32_10((b & MASK, b >> 32, self.env_id, self.stream), self.key)
+            self._blk = philox4x32_10(step_counter(self.t, b, self.env_id, self.stream), self.key)
             self._blk_idx = b
-        return self._blk[d & 3]
+        return self._blk[j & 3]
 
     def next_u32(self) -> int:
         w = self.word_at(self.ctr)
         self.ctr += 1
+        self.total += 1
         return w
 
     # --- the four entry points the reference calls -------------------------------

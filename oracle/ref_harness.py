@@ -136,9 +136,14 @@ class _NpProxy:
 class _MTStream:
     """stdlib-Mersenne-Twister stream with the DrawStream interface (timing runs only)."""
 
+    total = 0
+
     def __init__(self, seed):
         self._r = _stdlib_random.Random(seed)
         self._n = _np.random.RandomState(seed & 0x7FFFFFFF)
+
+    def begin_step(self, t):
+        pass
 
     def randint(self, a, b):
         return self._r.randint(int(a), int(b))
@@ -157,6 +162,10 @@ class _ConstStream:
     """The constant RNG of SURVEY.md Appendix A (RNG-free known-answer trace)."""
 
     ctr = 0
+    total = 0
+
+    def begin_step(self, t):
+        pass
 
     def randint(self, a, b):
         return int(a)
@@ -214,6 +223,7 @@ class RefEnvV0:
         self.shim.stream = self.stream
         self.env = self.fe.FutbolEnv(random_opp=random_opp, **kwargs)
         self.obs = self.env.reset()
+        self.t_total = 0   # steps since construction: the Philox step index (not cleared by reset)
 
     def reset(self):
         self.shim.stream = self.stream
@@ -222,6 +232,8 @@ class RefEnvV0:
 
     def step(self, action):
         self.shim.stream = self.stream
+        self.stream.begin_step(self.t_total)
+        self.t_total += 1
         self.obs, reward, done, info = self.env.step(action)
         return self.obs, reward, done, info
 
@@ -260,7 +272,7 @@ def rollout_v0(seed, env_id, steps, random_opp, actions=None, reset_on_done=True
         out["last_owner"][t] = env.last_owner
         out["ai_score"][t] = env.env.ai_score
         out["opp_score"][t] = env.env.opp_score
-        out["draws"][t] = getattr(env.stream, "ctr", 0)
+        out["draws"][t] = env.stream.total
         if d and reset_on_done:
             env.reset()
     return out

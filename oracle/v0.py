@@ -13,20 +13,22 @@ _LIB_PATH = os.path.join(_HERE, "libfutbol_oracle.so")
 
 class OracleV0Config(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("random_opp", C.c_int32), ("one_goal_end", C.c_int32),
-                ("only_reward_goal", C.c_int32), ("sq_mode", C.c_int32), ("rng_const", C.c_int32),
+                ("only_reward_goal", C.c_int32), ("arith", C.c_int32), ("rng_const", C.c_int32),
                 ("pad_", C.c_int32), ("game_time", C.c_double),
                 ("player_speed", C.c_double), ("shoot_speed", C.c_double)]
 
 
 class OracleV0Env(C.Structure):
     _fields_ = [("obs", (C.c_double * 5) * 6), ("kick", (C.c_double * 2) * 4), ("time", C.c_double),
-                ("draw_ctr", C.c_uint64), ("t_total", C.c_uint64), ("env_id", C.c_uint32),
+                ("draw_ctr", C.c_uint64), ("t_total", C.c_uint64), ("step_draws", C.c_uint32),
+                ("pad_", C.c_uint32), ("env_id", C.c_uint32),
                 ("owner", C.c_int32), ("last_owner", C.c_int32), ("ai_score", C.c_int32),
                 ("opp_score", C.c_int32), ("flags", C.c_int32)]
 
 
 ENV_DTYPE = np.dtype([("obs", np.float64, (6, 5)), ("kick", np.float64, (4, 2)), ("time", np.float64),
-                      ("draw_ctr", np.uint64), ("t_total", np.uint64), ("env_id", np.uint32),
+                      ("draw_ctr", np.uint64), ("t_total", np.uint64), ("step_draws", np.uint32),
+                      ("pad_", np.uint32), ("env_id", np.uint32),
                       ("owner", np.int32), ("last_owner", np.int32), ("ai_score", np.int32),
                       ("opp_score", np.int32), ("flags", np.int32)], align=True)
 
@@ -69,10 +71,10 @@ class OracleV0:
     """A batch of oracle envs with global ids env_id0 .. env_id0+n-1."""
 
     def __init__(self, n=1, seed=0, env_id0=0, random_opp=True, one_goal_end=False, only_reward_goal=False,
-                 game_time=40.0, player_speed=12.0, shoot_speed=20.0, sq_mode=1, rng_const=False):
+                 game_time=40.0, player_speed=12.0, shoot_speed=20.0, arith=1, rng_const=False):
         self.lib = lib()
         self.n = int(n)
-        self.cfg = OracleV0Config(seed, int(random_opp), int(one_goal_end), int(only_reward_goal), int(sq_mode),
+        self.cfg = OracleV0Config(seed, int(random_opp), int(one_goal_end), int(only_reward_goal), int(arith),
                                   int(rng_const), 0, float(game_time), float(player_speed), float(shoot_speed))
         self.envs = np.zeros(self.n, dtype=ENV_DTYPE)
         for i in range(self.n):

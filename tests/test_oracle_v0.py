@@ -14,10 +14,10 @@ from oracle.v0 import OracleV0, lib
 INT_FIELDS = ("done", "owner", "last_owner", "ai_score", "opp_score")
 
 
-def _run_case(case, sq_mode=1):
+def _run_case(case, arith=1):
     m = case["meta"]
     kw = m["kwargs"]
-    o = OracleV0(1, seed=m["seed"], env_id0=m["env_id"], random_opp=m["random_opp"], sq_mode=sq_mode,
+    o = OracleV0(1, seed=m["seed"], env_id0=m["env_id"], random_opp=m["random_opp"], arith=arith,
                  rng_const=(m["rng"] == "const"), one_goal_end=kw.get("one_goal_end", False),
                  only_reward_goal=kw.get("only_reward_goal", False), game_time=kw.get("game_time", 40.0))
     return o.rollout(m["steps"], actions=case["action"], autoreset=1)
@@ -66,10 +66,10 @@ def test_oracle_matches_reference_golden_bit_exact(golden_v0):
 
 
 def test_oracle_kernel_arithmetic_mode_within_tolerance(golden_v0):
-    """sq_mode=0 (x*x, what the CUDA kernel computes) vs the reference: ints exact, floats 1e-9."""
+    """arith=0 (x*x, what the CUDA kernel computes) vs the reference: ints exact, floats 1e-9."""
     worst = 0.0
     for name, case in golden_v0["cases"].items():
-        out = _run_case(case, sq_mode=0)
+        out = _run_case(case, arith=0)
         for f in INT_FIELDS:
             assert np.array_equal(out[f][:, 0], case[f]), (name, f)
         steps = case["meta"]["steps"]
@@ -127,3 +127,46 @@ def test_trajectory_independent_of_batch_position():
     one = OracleV0(1, seed=3, env_id0=1017, random_opp=False).rollout(200)
     assert np.array_equal(big["obs"][:, 17], one["obs"][:, 0])
     assert np.array_equal(big["reward"][:, 17], one["reward"][:, 0])
+
+
+def test_fm_functions_track_libm():
+    """The specified log/sin/cos of the kernel arithmetic stay within ~1 ulp of libm on their domains."""
+    import ctypes
+    import math
+    fm = lib().futbol_oracle_fm
+    fm.argtypes = [ctypes.c_double, ctypes.c_void_p]
+    out = np.zeros(3)
+    rng = np.random.RandomState(7)
+    xs = np.concatenate([rng.uniform(-6.3, 6.3, 20000), (rng.randint(1, 1 << 24, 20000)) / 16777216.0])
+    for x in xs:
+        fm(float(x), out.ctypes.data)
+        assert abs(out[1] - math.sin(x)) <= 4.5e-16 and abs(out[2] - math.cos(x)) <= 4.5e-16
+        if x > 0:
+            assert abs(out[0] - math.log(x)) <= 2.3e-16 * max(abs(math.log(x)), 1e-300) or x == 1.0
+
+
+def test_libm_mode_vs_kernel_mode_divergence_is_knife_edge_only():
+    """arith=1 (== Python reference) vs arith=0 (== CUDA kernel) on 2048 envs x 1000 steps.
+
+    Integers agree for nearly every env (measured on 8192 envs x 1000 steps: 0.5 % of the trajectories
+    split with random opponents, 3.2 % with the hard-coded ones, i.e. 5e-6 / 3e-5 per env-step); where an
+    env does split, the floats were still within 1e-11 on the step before: the split is decided by a
+    last-bit difference in a compare (the game has structural knife edges, e.g. an opponent chasing its
+    own shot closes by exactly 0.1 per step and is tested with ``distance <= 1``), not by logic.
+    """
+    n, steps = 2048, 1000
+    for random_opp in (True, False):
+        a = OracleV0(n, seed=17, random_opp=random_opp, arith=1).rollout(steps, autoreset=2, n_threads=8)
+        b = OracleV0(n, seed=17, random_opp=random_opp, arith=0).rollout(steps, autoreset=2, n_threads=8)
+        mism = np.zeros((steps, n), bool)
+        for f in INT_FIELDS:
+            mism |= a[f] != b[f]
+        err = np.abs(a["obs"] - b["obs"]).max(-1) / np.maximum(1.0, np.abs(a["obs"]).max(-1))
+        split = mism | (err > 1e-9)           # first step at which the two trajectories visibly part
+        diverged = split.any(0)
+        first = np.where(diverged, split.argmax(0), steps)
+        assert diverged.mean() <= 0.06, "more than 6 % of the 1000-step trajectories split"
+        for i in np.flatnonzero(diverged):
+            if first[i] > 0:
+                assert err[first[i] - 1, i] <= 1e-11, (i, first[i])
+        assert err[:, ~diverged].max() <= 1e-9
