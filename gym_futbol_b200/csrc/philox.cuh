@@ -11,6 +11,7 @@ constexpr uint32_t kStreamDynamics = 0;   // v0 environment draws
 constexpr uint32_t kStreamActions = 1;    // synthetic AI actions (bench / in-kernel random policy)
 constexpr uint32_t kStreamV1Opp = 2;      // v1 opponent actions
 constexpr uint32_t kStreamV1Dynamics = 3; // v1 environment draws
+constexpr uint32_t kNormalBlock0 = 0x8000u; // first Philox block of a step's normal() slots
 
 struct Philox4 { uint32_t x, y, z, w; };
 
@@ -44,11 +45,11 @@ template <int kPreBlocks>
 struct StepRng {
     uint32_t w[kPreBlocks * 4];
     uint64_t seed, t;
-    uint32_t env_id, stream, j;
+    uint32_t env_id, stream, j, normal_calls;
 
     __device__ __forceinline__ void begin(uint64_t seed_, uint32_t env_id_, uint32_t stream_, uint64_t t_)
     {
-        seed = seed_; env_id = env_id_; stream = stream_; t = t_; j = 0;
+        seed = seed_; env_id = env_id_; stream = stream_; t = t_; j = 0; normal_calls = 0;
 #pragma unroll
         for (int b = 0; b < kPreBlocks; ++b) {
             const Philox4 p = philox_step_block(seed, env_id, stream, t, b);

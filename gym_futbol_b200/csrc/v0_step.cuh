@@ -137,15 +137,17 @@ __device__ __forceinline__ int defence_near(const V0State &s, const V0Params &P)
     return within_count(hyp(dsub(d1.x, vx), dsub(d1.y, vy)), hyp(dsub(d2.x, vx), dsub(d2.y, vy)));
 }
 
-// screw_vec, :101-116.  The reference draws 10 normals and then an index; only the indexed slot is
-// evaluated here (draw layout: slot k = draws base+2k, base+2k+1; index = draw base+20).
+// screw_vec, :101-116.  The reference draws 10 normals (np.random.normal(0, accuracy, 10), :103) and
+// then an index (randint(0, 9), :107).  By specification (oracle/philox.py) the c-th normal() call of a
+// step consumes no sequential draws: slot k lives in Philox block 0x8000 + 8c + (k >> 1), words
+// 2(k&1), 2(k&1)+1, so only the block of the indexed slot is evaluated here.
 __device__ __forceinline__ void screw_vec(V0Rng &rng, double vx, double vy, double mag, double accuracy,
                                           double &ox, double &oy)
 {
-    const uint32_t base = rng.j;
-    const uint32_t pick = __umulhi(rng.word_at(base + 20), 10u);         // randint(0, 9), :107
-    const uint32_t w0 = rng.word_at(base + 2 * pick), w1 = rng.word_at(base + 2 * pick + 1);
-    rng.j = base + 21;
+    const uint32_t call = rng.normal_calls++;
+    const uint32_t pick = (uint32_t)rng.randint(0, 9);                   // :107
+    const Philox4 nb = philox_step_block(rng.seed, rng.env_id, rng.stream, rng.t, kNormalBlock0 + 8u * call + (pick >> 1));
+    const uint32_t w0 = (pick & 1u) ? nb.z : nb.x, w1 = (pick & 1u) ? nb.w : nb.y;
     const double u1 = (double)((w0 >> 8) + 1u) * (1.0 / 16777216.0);
     const double u2 = (double)(w1 >> 8) * (1.0 / 16777216.0);
     double bm_sin, bm_cos;

@@ -85,7 +85,7 @@ typedef struct {
     uint64_t draw_ctr;   /* draws consumed since construction (bookkeeping only) */
     uint64_t t_total;    /* total steps taken = Philox step index; not cleared by reset */
     uint32_t step_draws; /* draws consumed inside the current step (index j of the next draw) */
-    uint32_t pad_;
+    uint32_t normal_calls; /* normal() calls inside the current step */
     uint32_t env_id;     /* global env id */
     int32_t owner, last_owner;
     int32_t ai_score, opp_score;
@@ -208,12 +208,17 @@ static double rng_uniform(Ctx *c, double a, double b)
     if (c->cfg->rng_const) { next_u32(c); return (a + b) / 2; }
     return a + (b - a) * rng_random(c);
 }
+/* normal(mu, sd, 10): slot k comes from block 0x8000 + 8*call + (k >> 1), words 2(k&1), 2(k&1)+1;
+ * no sequential draws are consumed (specification: oracle/philox.py) */
 static void rng_normal10(Ctx *c, double mu, double sd, double out[10])
 {
-    if (c->cfg->rng_const) { c->e->draw_ctr += 20; c->e->step_draws += 20; for (int j = 0; j < 10; ++j) out[j] = 0.0; return; }
-    for (int j = 0; j < 10; ++j) {
-        double u1 = (double)((next_u32(c) >> 8) + 1u) * (1.0 / 16777216.0);
-        double u2 = (double)(next_u32(c) >> 8) * (1.0 / 16777216.0);
+    const uint32_t base = 0x8000u + 8u * c->e->normal_calls++;
+    if (c->cfg->rng_const) { for (int j = 0; j < 10; ++j) out[j] = 0.0; return; }
+    for (int k = 0; k < 10; ++k) {
+        uint32_t w0 = draw_word(c->cfg->seed, c->e->env_id, 0, c->e->t_total, 4u * (base + (uint32_t)(k >> 1)) + 2u * (k & 1));
+        uint32_t w1 = draw_word(c->cfg->seed, c->e->env_id, 0, c->e->t_total, 4u * (base + (uint32_t)(k >> 1)) + 2u * (k & 1) + 1u);
+        double u1 = (double)((w0 >> 8) + 1u) * (1.0 / 16777216.0);
+        double u2 = (double)(w1 >> 8) * (1.0 / 16777216.0);
         double z;
         if (c->cfg->arith) {
             z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
@@ -222,7 +227,7 @@ static void rng_normal10(Ctx *c, double mu, double sd, double out[10])
             fm_sincos(6.283185307179586 * u2, &sn, &cs);
             z = sqrt(-2.0 * fm_log(u1)) * cs;
         }
-        out[j] = mu + sd * z;
+        out[k] = mu + sd * z;
     }
 }
 
@@ -627,6 +632,7 @@ int futbol_v0_oracle_step(const OracleV0Config *cfg, OracleV0Env *e, int ai_acti
     memcpy(o_owner, e->obs[OWNER_ROW], sizeof(o_owner));
     e->flags = 0;
     e->step_draws = 0;
+    e->normal_calls = 0;
 
     if (cfg->random_opp) {                                  /* :639-645 */
         int r = rng_randint(c, 0, 15);

@@ -38,7 +38,10 @@ Draw -> value maps (``w`` = one 32-bit draw):
   random()        = (w >> 8) * 2**-24                        in [0, 1)
   randint(a, b)   = a + ((w * (b - a + 1)) >> 32)            a..b inclusive
   uniform(a, b)   = a + (b - a) * random()                   (CPython's formula)
-  normal(mu,sd,n) = reserves 2n draws; slot j uses draws (2j, 2j+1):
+  normal(mu,sd,n) = consumes NO sequential draws: the c-th normal() call of a step takes slot k
+                    (k < n <= 16) from block 0x8000 + 8c + (k >> 1), words (w0, w1) =
+                    (2(k&1), 2(k&1)+1) of that block (so a consumer that needs a single slot
+                    evaluates one Philox block):
                     u1 = ((w0 >> 8) + 1) * 2**-24   in (0, 1]
                     u2 =  (w1 >> 8)      * 2**-24   in [0, 1)
                     z  = sqrt(-2 ln u1) * cos(2 pi u2);   value = mu + sd * z
@@ -60,6 +63,7 @@ STREAM_DYNAMICS = 0
 STREAM_ACTIONS = 1
 STREAM_V1_OPP = 2
 STREAM_V1_DYNAMICS = 3
+NORMAL_BLOCK0 = 0x8000
 
 TWO_PI = 6.283185307179586
 INV_2_24 = 1.0 / 16777216.0
@@ -137,7 +141,7 @@ class DrawStream:
     draws consumed so far inside the current step, ``total`` since construction.
     """
 
-    __slots__ = ("key", "env_id", "stream", "t", "ctr", "total", "_blk_idx", "_blk", "log")
+    __slots__ = ("key", "env_id", "stream", "t", "ctr", "total", "normal_calls", "_blk_idx", "_blk", "log")
 
     def __init__(self, seed: int, env_id: int, stream: int = STREAM_DYNAMICS):
         self.key = seed_key(seed)
@@ -146,6 +150,7 @@ class DrawStream:
         self.t = 0
         self.ctr = 0
         self.total = 0
+        self.normal_calls = 0
         self._blk_idx = None
         self._blk = None
         self.log = None  # set to a list to record (kind, value) per call
@@ -153,6 +158,7 @@ class DrawStream:
     def begin_step(self, t: int):
         self.t = int(t)
         self.ctr = 0
+        self.normal_calls = 0
         self._blk_idx = None
 
     def word_at(self, j: int) -> int:
@@ -191,12 +197,18 @@ class DrawStream:
         return v
 
     def normal(self, mu, sd, n):
-        out = np.empty(int(n), dtype=np.float64)
-        for j in range(int(n)):
-            u1 = ((self.next_u32() >> 8) + 1) * INV_2_24
-            u2 = (self.next_u32() >> 8) * INV_2_24
+        n = int(n)
+        assert n <= 16
+        out = np.empty(n, dtype=np.float64)
+        base = NORMAL_BLOCK0 + 8 * self.normal_calls
+        self.normal_calls += 1
+        for k in range(n):
+            blk = philox4x32_10(step_counter(self.t, base + (k >> 1), self.env_id, self.stream), self.key)
+            w0, w1 = blk[2 * (k & 1)], blk[2 * (k & 1) + 1]
+            u1 = ((w0 >> 8) + 1) * INV_2_24
+            u2 = (w1 >> 8) * INV_2_24
             z = math.sqrt(-2.0 * math.log(u1)) * math.cos(TWO_PI * u2)
-            out[j] = mu + sd * z
+            out[k] = mu + sd * z
         if self.log is not None:
             self.log.append(("normal", out.copy()))
         return out

@@ -21,14 +21,14 @@ class OracleV0Config(C.Structure):
 class OracleV0Env(C.Structure):
     _fields_ = [("obs", (C.c_double * 5) * 6), ("kick", (C.c_double * 2) * 4), ("time", C.c_double),
                 ("draw_ctr", C.c_uint64), ("t_total", C.c_uint64), ("step_draws", C.c_uint32),
-                ("pad_", C.c_uint32), ("env_id", C.c_uint32),
+                ("normal_calls", C.c_uint32), ("env_id", C.c_uint32),
                 ("owner", C.c_int32), ("last_owner", C.c_int32), ("ai_score", C.c_int32),
                 ("opp_score", C.c_int32), ("flags", C.c_int32)]
 
 
 ENV_DTYPE = np.dtype([("obs", np.float64, (6, 5)), ("kick", np.float64, (4, 2)), ("time", np.float64),
                       ("draw_ctr", np.uint64), ("t_total", np.uint64), ("step_draws", np.uint32),
-                      ("pad_", np.uint32), ("env_id", np.uint32),
+                      ("normal_calls", np.uint32), ("env_id", np.uint32),
                       ("owner", np.int32), ("last_owner", np.int32), ("ai_score", np.int32),
                       ("opp_score", np.int32), ("flags", np.int32)], align=True)
 

@@ -275,10 +275,10 @@ def test_divergence_growth_report(torch_cuda):
             o = obs.cpu().numpy()
             err[t] = (np.abs(o - want["obs"][t]) / np.maximum(1.0, np.abs(want["obs"][t]))).max(-1)
             mism[t] = (done.cpu().numpy() != want["done"][t]) | (np.argmax(o[:, 25:], -1) != np.argmax(want["obs"][t][:, 25:], -1))
-        split = (mism | (err > 1e-9)).any(0)
+        split = (mism | (err > 1e-6)).any(0)
         assert split.mean() <= 0.08
         together = err[:, ~split]
-        assert together.max() <= 1e-9                       # north_star allows 1e-4 after 1000 steps
+        assert together.max() <= 1e-7                       # north_star allows 1e-4 after 1000 steps
         report["random_opp=%s" % random_opp] = {
             "trajectories": n, "split_at_last_bit_compare": int(split.sum()),
             "max_rel_err_by_step_of_the_rest": {str(t + 1): float(together[:t + 1].max()) for t in (0, 9, 99, 399, 999)}}
