@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <math.h>
 #include <new>
 #include "../../include/futbol_b200.h"
 #include "v0_kernels.h"
@@ -35,6 +36,17 @@ static int episode_limit(double game_time)
     int k = 0;
     while (!(t >= game_time) && k < (1 << 30)) { t += 0.1; ++k; }
     return k;
+}
+
+// Largest double s with sqrt(s) < r (IEEE sqrt is correctly rounded, hence monotone), or -1 if none:
+// lets the kernel test `sqrt(s) < r` as `s <= bound` without taking the root.
+static double sqrt_less_than_bound(double r)
+{
+    if (!(r > 0.0)) return -1.0;
+    double s = r * r;
+    while (sqrt(s) >= r) s = nextafter(s, -INFINITY);
+    while (sqrt(nextafter(s, INFINITY)) < r) s = nextafter(s, INFINITY);
+    return s;
 }
 
 extern "C" {
@@ -71,6 +83,7 @@ int futbol_create(const FutbolConfig *cfg, FutbolHandle **out)
     P.ep_limit = episode_limit(cfg->game_time);
     P.shoot_speed = cfg->shoot_speed;
     P.player_speed = cfg->player_speed;
+    P.reach_sq_max = sqrt_less_than_bound(0.1 * cfg->player_speed);   // futbol_env.py:972 `< STEP_SIZE * player_speed`
     *out = h;
     return FUTBOL_OK;
 }

@@ -13,6 +13,13 @@ constexpr uint32_t kStreamV1Opp = 2;      // v1 opponent actions
 constexpr uint32_t kStreamV1Dynamics = 3; // v1 environment draws
 constexpr uint32_t kNormalBlock0 = 0x8000u; // first Philox block of a step's normal() slots
 
+// Threads per block of every kernel that steps environments = stride of the shared-memory draw buffer.
+#ifndef FUTBOL_ENV_THREADS
+#define FUTBOL_ENV_THREADS 128
+#endif
+constexpr int kEnvThreads = FUTBOL_ENV_THREADS;
+constexpr int kPreDraws = 8;              // draws generated up front per step (2 Philox blocks)
+
 struct Philox4 { uint32_t x, y, z, w; };
 
 __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -39,44 +46,55 @@ __device__ __forceinline__ Philox4 philox_step_block(uint64_t seed, uint32_t env
                          (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
-// The sequential per-step draw stream.  The first kPre*4 words are produced up front by every
-// lane (uniform control flow); later words (only the rare "shoot" path reaches them) on demand.
-template <int kPreBlocks>
-struct StepRng {
-    uint32_t w[kPreBlocks * 4];
-    uint64_t seed, t;
-    uint32_t env_id, stream, j, normal_calls;
+// draws past the pre-generated ones: out of line, a step needs at most 10 and almost always <= 8
+static __device__ __noinline__ uint32_t philox_step_word(uint64_t seed, uint32_t env_id, uint32_t stream, uint64_t t,
+                                                         uint32_t idx)
+{
+    const Philox4 p = philox_step_block(seed, env_id, stream, t, idx >> 2);
+    const uint32_t lo = (idx & 1u) ? p.y : p.x, hi = (idx & 1u) ? p.w : p.z;
+    return (idx & 2u) ? hi : lo;
+}
 
-    __device__ __forceinline__ void begin(uint64_t seed_, uint32_t env_id_, uint32_t stream_, uint64_t t_)
+// The sequential per-step draw stream.  The reference consumes a state-dependent number of draws in
+// a state-dependent order, so the position `j` of the next draw is data; a register array indexed by
+// data would cost a select tree per draw (or live in local memory).  The first kPreDraws words of the
+// step are therefore parked in shared memory, one column per thread (word k of thread `tid` at
+// buf[k * kEnvThreads + tid]: every lane hits its own bank whatever its j), and a draw is one LDS.
+struct StepRng {
+    const uint32_t *col;
+    uint64_t seed, t;
+    uint32_t env_id, stream, j;
+
+    __device__ __forceinline__ void begin(uint32_t *col_, uint64_t seed_, uint32_t env_id_, uint32_t stream_, uint64_t t_)
     {
-        seed = seed_; env_id = env_id_; stream = stream_; t = t_; j = 0; normal_calls = 0;
+        col = col_; seed = seed_; env_id = env_id_; stream = stream_; t = t_; j = 0;
 #pragma unroll
-        for (int b = 0; b < kPreBlocks; ++b) {
+        for (int b = 0; b < kPreDraws / 4; ++b) {
             const Philox4 p = philox_step_block(seed, env_id, stream, t, b);
-            w[4 * b + 0] = p.x; w[4 * b + 1] = p.y; w[4 * b + 2] = p.z; w[4 * b + 3] = p.w;
+            col_[(4 * b + 0) * kEnvThreads] = p.x; col_[(4 * b + 1) * kEnvThreads] = p.y;
+            col_[(4 * b + 2) * kEnvThreads] = p.z; col_[(4 * b + 3) * kEnvThreads] = p.w;
         }
     }
 
     __device__ __forceinline__ uint32_t word_at(uint32_t idx) const
     {
-        if (idx < (uint32_t)(kPreBlocks * 4)) {
-            // register select tree (a dynamically indexed array would live in local memory)
-            uint32_t r = w[0];
-#pragma unroll
-            for (int i = 1; i < kPreBlocks * 4; ++i) r = (idx == (uint32_t)i) ? w[i] : r;
-            return r;
-        }
-        const Philox4 p = philox_step_block(seed, env_id, stream, t, idx >> 2);
-        const uint32_t lo = (idx & 1u) ? p.y : p.x, hi = (idx & 1u) ? p.w : p.z;
-        return (idx & 2u) ? hi : lo;
+        if (idx < (uint32_t)kPreDraws) return col[idx * kEnvThreads];
+        return philox_step_word(seed, env_id, stream, t, idx);
     }
 
-    __device__ __forceinline__ uint32_t next_u32() { return word_at(j++); }
-    // random.random(): (w >> 8) * 2^-24
-    __device__ __forceinline__ double random() { return (double)(next_u32() >> 8) * (1.0 / 16777216.0); }
-    // random.randint(a, b): a + ((w * (b - a + 1)) >> 32)
-    __device__ __forceinline__ int randint(int a, int b) { return a + (int)__umulhi(next_u32(), (uint32_t)(b - a + 1)); }
+    __device__ __forceinline__ uint32_t take() { return word_at(j++); }
+    // the word at the cursor; consumed only if `c` (the value is ignored by the caller otherwise)
+    __device__ __forceinline__ uint32_t take_if(bool c)
+    {
+        uint32_t w = 0;
+        if (j < (uint32_t)kPreDraws) w = col[j * kEnvThreads];
+        else if (c) w = philox_step_word(seed, env_id, stream, t, j);
+        j += c ? 1u : 0u;
+        return w;
+    }
 };
+
+typedef StepRng V0Rng;
 
 __device__ __forceinline__ int philox_action(uint64_t seed, uint32_t env_id, uint64_t t, uint32_t n_actions)
 {

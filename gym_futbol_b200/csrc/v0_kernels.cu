@@ -115,15 +115,16 @@ __global__ void __launch_bounds__(128) v0_reset_kernel(V0Params P, StateView v, 
 }
 
 // ---- per-step API ----------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(128) v0_step_kernel(V0Params P, StateView v, const uint8_t *actions, T *obs,
-                                                      T *reward, uint8_t *done, T *final_obs)
+template <typename T, bool RANDOM_OPP>
+__global__ void __launch_bounds__(kEnvThreads) v0_step_kernel(V0Params P, StateView v, const uint8_t *actions, T *obs,
+                                                              T *reward, uint8_t *done, T *final_obs)
 {
+    __shared__ uint32_t draws[kPreDraws * kEnvThreads];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_envs) return;
     V0State s;
     load_state(v, i, s);
-    const StepResult r = v0_step(s, P, P.env_id_offset + (uint32_t)i, actions[i] & 15);
+    const StepResult r = v0_step<RANDOM_OPP>(s, P, P.env_id_offset + (uint32_t)i, actions[i] & 15, draws + threadIdx.x);
     if (r.done && P.auto_reset) {
         if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * kObsDim, s);
         reset_env(s);
@@ -135,13 +136,15 @@ __global__ void __launch_bounds__(128) v0_step_kernel(V0Params P, StateView v, c
 }
 
 // ---- fused K-step rollout ----------------------------------------------------------------------------
-constexpr int kRolloutThreads = 128;
+constexpr int kRolloutThreads = kEnvThreads;
 
+template <bool RANDOM_OPP>
 __global__ void __launch_bounds__(kRolloutThreads)
 v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ actions, float *__restrict__ obs,
                   float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
 {
     __shared__ __align__(16) float stage[kRolloutThreads / 32][32 * kObsDim];
+    __shared__ uint32_t draws[kPreDraws * kEnvThreads];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warp_env0 = i - lane;
@@ -167,7 +170,7 @@ v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ ac
         if (actions != nullptr) a = live ? (__ldg(actions + slot) & 15) : 0;
         else a = philox_action(P.seed, env_id, s.t_total, 16);
         const int ai_before = s.ai_score;
-        const StepResult r = v0_step(s, P, env_id, a);
+        const StepResult r = v0_step<RANDOM_OPP>(s, P, env_id, a, draws + threadIdx.x);
         last_flags = r.flags;
         reward_sum += r.reward;
         goals_ai += (r.flags & kFlagGoal) && s.ai_score != ai_before;
@@ -239,16 +242,25 @@ cudaError_t v0_launch_reset(const V0Params &P, void *state, const uint8_t *mask,
     return cudaGetLastError();
 }
 
+template <typename T, bool RANDOM_OPP>
+static void launch_step(const V0Params &P, const StateView &v, const uint8_t *actions, void *obs, void *reward,
+                        uint8_t *done, void *final_obs, cudaStream_t st)
+{
+    v0_step_kernel<T, RANDOM_OPP><<<blocks_for(P.n_envs, kEnvThreads), kEnvThreads, 0, st>>>(P, v, actions, (T *)obs, (T *)reward,
+                                                                                         done, (T *)final_obs);
+}
+
 cudaError_t v0_launch_step(const V0Params &P, void *state, const uint8_t *actions, void *obs, void *reward,
                            uint8_t *done, void *final_obs, int out_f64, cudaStream_t st)
 {
     const StateView v = make_view(state, P.n_envs);
-    if (out_f64)
-        v0_step_kernel<double><<<blocks_for(P.n_envs, 128), 128, 0, st>>>(P, v, actions, (double *)obs, (double *)reward,
-                                                                          done, (double *)final_obs);
-    else
-        v0_step_kernel<float><<<blocks_for(P.n_envs, 128), 128, 0, st>>>(P, v, actions, (float *)obs, (float *)reward,
-                                                                         done, (float *)final_obs);
+    if (out_f64) {
+        if (P.random_opp) launch_step<double, true>(P, v, actions, obs, reward, done, final_obs, st);
+        else launch_step<double, false>(P, v, actions, obs, reward, done, final_obs, st);
+    } else {
+        if (P.random_opp) launch_step<float, true>(P, v, actions, obs, reward, done, final_obs, st);
+        else launch_step<float, false>(P, v, actions, obs, reward, done, final_obs, st);
+    }
     return cudaGetLastError();
 }
 
@@ -256,8 +268,9 @@ cudaError_t v0_launch_rollout(const V0Params &P, void *state, int K, const uint8
                               uint8_t *done, FutbolStats *stats, cudaStream_t st)
 {
     const StateView v = make_view(state, P.n_envs);
-    v0_rollout_kernel<<<blocks_for(P.n_envs, kRolloutThreads), kRolloutThreads, 0, st>>>(P, v, K, actions, obs, reward,
-                                                                                         done, stats);
+    const int blocks = blocks_for(P.n_envs, kRolloutThreads);
+    if (P.random_opp) v0_rollout_kernel<true><<<blocks, kRolloutThreads, 0, st>>>(P, v, K, actions, obs, reward, done, stats);
+    else v0_rollout_kernel<false><<<blocks, kRolloutThreads, 0, st>>>(P, v, K, actions, obs, reward, done, stats);
     return cudaGetLastError();
 }
 

@@ -7,6 +7,17 @@
 // fuses), IEEE sqrt/div.  Numpy-scalar x**2 is computed as x*x, and log/sin/cos are the fully
 // specified fm_log/fm_sincos below (fdlibm-style polynomials, individually rounded IEEE operations in a
 // fixed order), so that a CPU restatement of the same specification agrees BIT for bit.
+//
+// Shape of the code ("branch-lean").  The reference picks one of eight branches per player
+// (has-ball x action); the 32 environments of a warp pick 32 different ones, so a branchy transcription
+// executes the union of all branches at ~13 active lanes and, inlined four times, overflows the 32 KB
+// instruction cache (ncu: 76 % of stall samples "no instruction").  Here every player turn is ONE
+// straight-line block: the case is classified into predicates, the single vector magnitude any case
+// needs is computed once, results are committed with selects.  What stays behind a branch is rare:
+// the kick (screw_vec: log, sin, cos) -- deferred to one shared site per step because at most one player
+// can shoot per step -- and draws past the eight pre-generated Philox words.  Threshold tests on a
+// distance (d <= 2, d > 12, ...) are done on the squared distance with the exactly equivalent bound
+// (kSq* below), which removes the square root without changing a single decision.
 #pragma once
 #include <stdint.h>
 #include "philox.cuh"
@@ -21,7 +32,24 @@ enum : int { kFlagGoal = 1, kFlagFix = 2, kFlagDone = 4 };
 constexpr double kFieldLen = 105.0, kFieldWid = 68.0;   // futbol_env.py:18-19
 constexpr double kGoalLower = 29.0, kGoalUpper = 39.0;  // :23-24
 constexpr double kStepSize = 0.1;                       // :45
-constexpr int kV0PreBlocks = 2;                         // 8 draws cover every non-shoot step (>99.9 %)
+
+// For s = fl(fl(dx*dx) + fl(dy*dy)) and d = sqrt_rn(s) (correctly rounded, hence monotone):
+//   d <= 1.0  <=>  s <= nextafter(1, +inf)
+//   d <= 2.0  <=>  s <= nextafter(4, +inf)
+//   d > 12.0  <=>  s >  144.0
+// (sqrt(s) rounds to c or below exactly when it lies below the midpoint of c and its successor; squaring
+// that midpoint gives the bound.  tests/test_sqrt_thresholds.py checks every neighbouring double.)
+constexpr double kSqLe1 = 0x1.0000000000001p+0;
+constexpr double kSqLe2 = 0x1.0000000000001p+2;
+constexpr double kSqGt12 = 144.0;
+// products of reference constants, rounded once as the reference's float64 multiply rounds them
+// (__dmul_rn is not folded by the compiler; tests/test_sqrt_thresholds.py::test_constant_products)
+constexpr double kWid02 = 13.600000000000001;   // width * 0.2, :895
+constexpr double kWid08 = 54.400000000000006;   // width * 0.8, :913
+constexpr double kLen01 = 10.5;                 // length * 0.1, :903
+constexpr double kLen06 = 63.0;                 // length * 0.6, :931
+constexpr double kDefendX = 78.75, kDefendY = 34.0;   // (length * 0.75, width * 0.5), :933
+constexpr double kRewStolen = -15.0, kRewGained = 18.0, kRewKept = 9.0;   // -50*0.3, 60*0.3, 30*0.3, :832-839
 
 struct Row { double x, y, tx, ty, sp; };
 
@@ -30,9 +58,10 @@ struct V0Params {
     uint32_t env_id_offset;
     int n_envs;
     int random_opp, one_goal_end, only_reward_goal, auto_reset;
-    int ep_limit;       // first ep_step at which `time >= game_time` holds (400 for game_time 40)
+    int ep_limit;        // first ep_step at which `time >= game_time` holds (400 for game_time 40)
     int shoot_speed;
     double player_speed;
+    double reach_sq_max; // largest s with sqrt_rn(s) < fl(0.1 * player_speed) (:972-976); set by the host
 };
 
 struct V0State {
@@ -42,13 +71,12 @@ struct V0State {
     int ep_step, ai_score, opp_score, owner, last_owner;
 };
 
-typedef StepRng<kV0PreBlocks> V0Rng;
-
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
-__device__ __forceinline__ double hyp(double vx, double vy) { return __dsqrt_rn(dadd(dmul(vx, vx), dmul(vy, vy))); }
+__device__ __forceinline__ double sqsum(double vx, double vy) { return dadd(dmul(vx, vx), dmul(vy, vy)); }
+__device__ __forceinline__ double hyp(double vx, double vy) { return __dsqrt_rn(sqsum(vx, vy)); }   // get_vec, :62-65
 
 // ---- specified elementary functions (domain: log on (0,1]; sin/cos on |x| <= 2*pi) --------------------
 __device__ __forceinline__ double fm_log(double x)
@@ -117,120 +145,114 @@ __device__ __forceinline__ void reset_env(V0State &s)
     s.opp_score = 0;
 }
 
-// bigger_than(x1, x2, 2), :76-82
-__device__ __forceinline__ int within_count(double d1, double d2)
-{
-    return (d1 <= 2.0 && d2 <= 2.0) ? 2 : ((d1 > 2.0 && d2 > 2.0) ? 0 : 1);
-}
+// A kick waiting to be resolved.  At most one player can shoot in a step: shooting needs the ball at
+// the player's own turn, a shot leaves the ball with no one, and the only way to gain it back inside
+// the step is an intercept -- which is that player's single action of the step (for the hard-coded
+// opponents has_ball is latched before either acts, :866-877, and cannot hold for both).  So the
+// expensive part of shoot (defence_near + screw_vec, :364-378) is evaluated once per step, after the
+// last player turn: everything it reads (player and ball POSITIONS) only changes in the kinematics
+// phase, and the vector it writes is first read there.  A later successful intercept overwrites the
+// whole ball row (:465-466), which cancels the pending kick.
+struct PendingShot { int shooter; int target_y; uint32_t pick_idx; };
 
-// defence_near, :280-289, with the stale-view behaviour: the shooter's own position is
-// the frozen kickoff spot, except for hard-coded opponents whose views are refreshed every step.
+// _set_vector_observation, :300-530, for one player: straight-line, predicated.
 template <int AGENT>
-__device__ __forceinline__ int defence_near(const V0State &s, const V0Params &P)
+__device__ __forceinline__ void player_turn(V0State &s, V0Rng &rng, const V0Params &P, bool has_ball, int action,
+                                            bool set_target, double tgx, double tgy, PendingShot &shot)
 {
     constexpr bool right = AGENT >= kOpp1;
-    double vx = (AGENT == kAI1 || AGENT == kAI2) ? kFieldLen / 2 - 9 : kFieldLen / 2 + 9;
-    double vy = (AGENT == kAI1 || AGENT == kOpp1) ? kFieldWid / 2 + 5 : kFieldWid / 2 - 5;
-    if (right && !P.random_opp) { vx = s.p[AGENT].x; vy = s.p[AGENT].y; }
-    const Row &d1 = right ? s.p[kAI1] : s.p[kOpp1];
-    const Row &d2 = right ? s.p[kAI2] : s.p[kOpp2];
-    return within_count(hyp(dsub(d1.x, vx), dsub(d1.y, vy)), hyp(dsub(d2.x, vx), dsub(d2.y, vy)));
+    constexpr double goal_x = right ? 0.0 : kFieldLen;
+    Row &ao = s.p[AGENT];
+    const Row &mate = s.p[AGENT ^ 1];
+
+    const int target_y = 32 + (int)__umulhi(rng.take(), 5u);             // randint(32, 36), :306 -- always drawn first
+    const bool is_run = action == kRun, is_int = action == kIntercept;
+    const bool hb_run = has_ball && is_run, hb_int = has_ball && is_int;
+    const bool hb_shoot = has_ball && action == kShoot, hb_assist = has_ball && action == kAssist;
+    const bool nb_int = !has_ball && is_int;
+    // one more draw in: has-ball run (:353), shoot (:367), assist (:416); no-ball intercept (:459, even when far)
+    const uint32_t w = rng.take_if(has_ball != is_int);
+    const double u = (double)(w >> 8) * (1.0 / 16777216.0);
+
+    const double bx = dsub(s.b.x, ao.x), by = dsub(s.b.y, ao.y);         // :432
+    const double vx = hb_assist ? dsub(mate.x, s.b.x) : bx;              // :412
+    const double vy = hb_assist ? dsub(mate.y, s.b.y) : by;
+    const double mag = hyp(vx, vy);                                      // the one magnitude a turn needs
+
+    // has-ball assist, :413-416
+    double pass = ddiv(mag, kStepSize);
+    pass = pass > 20.0 ? 20.0 : pass;
+    const double lo = dsub(pass, 1.0), hi = dadd(pass, 1.0);
+    const double pass_speed = dadd(lo, dmul(dsub(hi, lo), u));           // random.uniform
+    // no-ball intercept, :452-463; intercept_chance(d, 1, 2) :122-129 with k = 0.9 / (1 - 2) = -0.9 exactly
+    const double chance = mag < 1.0 ? 0.9 : (mag <= 2.0 ? dmul(-0.9, dsub(mag, 2.0)) : 0.0);
+    const bool take = nb_int && (u < chance || (s.owner == kNoOne && mag < 4.0));
+    // has-ball run, :353-356 (Q3)
+    const bool drop = hb_run && u < 0.05;
+    const bool carry = hb_run && !drop;
+
+    // the player's own row (Q4: a no-ball intercept keeps the previous vector and speed)
+    if (is_run) {                                                        // :330-352, :483-503 (:503 unreachable, Q12)
+        ao.sp = P.player_speed;
+        ao.tx = set_target ? tgx : (has_ball ? dsub(goal_x, ao.x) : bx);
+        ao.ty = set_target ? tgy : (has_ball ? dsub((double)target_y, ao.y) : by);
+    } else if (!nb_int) {
+        zero_motion(ao);                                                 // :318-321, :383, :423, :509-525
+    }
+    // ball and possession
+    if (carry || take) s.b = ao;                                         // :356, :465-466
+    if (hb_int) zero_motion(s.b);                                        // :321
+    if (hb_assist) { s.b.sp = pass_speed; s.b.tx = vx; s.b.ty = vy; }    // :416-418
+    if (hb_shoot) {                                                      // :367; vector resolved later (PendingShot)
+        s.b.sp = (double)(P.shoot_speed - 16 + (int)__umulhi(w, 17u));
+        shot.shooter = AGENT; shot.target_y = target_y; shot.pick_idx = rng.j;
+        rng.j += 1;                                                      // randint(0, 9) of screw_vec, :107
+    }
+    if (take) shot.shooter = -1;
+    if (hb_shoot || hb_assist || take) s.last_owner = s.owner;           // :381, :421, :467
+    s.owner = take ? (int)AGENT : ((drop || hb_shoot || hb_assist) ? (int)kNoOne : s.owner);   // :354, :382, :422, :468
 }
 
-// screw_vec, :101-116.  The reference draws 10 normals (np.random.normal(0, accuracy, 10), :103) and
-// then an index (randint(0, 9), :107).  By specification (oracle/philox.py) the c-th normal() call of a
-// step consumes no sequential draws: slot k lives in Philox block 0x8000 + 8c + (k >> 1), words
-// 2(k&1), 2(k&1)+1, so only the block of the indexed slot is evaluated here.
-__device__ __forceinline__ void screw_vec(V0Rng &rng, double vx, double vy, double mag, double accuracy,
-                                          double &ox, double &oy)
+// defence_near (:280-289, with the stale-view behaviour Q1) + screw_vec (:101-116) for the pending kick.
+// By specification (oracle/philox.py) a step's normal() call consumes no sequential draws: slot k lives in
+// Philox block 0x8000 + (k >> 1), words 2(k&1), 2(k&1)+1, so only the block of the picked slot is evaluated.
+__device__ __forceinline__ void resolve_shot(V0State &s, const V0Rng &rng, const V0Params &P, const PendingShot &shot)
 {
-    const uint32_t call = rng.normal_calls++;
-    const uint32_t pick = (uint32_t)rng.randint(0, 9);                   // :107
-    const Philox4 nb = philox_step_block(rng.seed, rng.env_id, rng.stream, rng.t, kNormalBlock0 + 8u * call + (pick >> 1));
+    const int a = shot.shooter;
+    const bool right = a >= kOpp1;
+    // the shooter's own position is the frozen kickoff spot, except for hard-coded opponents (views refreshed)
+    double px = right ? kFieldLen / 2 + 9 : kFieldLen / 2 - 9;
+    double py = (a == kAI1 || a == kOpp1) ? kFieldWid / 2 + 5 : kFieldWid / 2 - 5;
+    if (right && !P.random_opp) {
+        px = a == kOpp1 ? s.p[kOpp1].x : s.p[kOpp2].x;
+        py = a == kOpp1 ? s.p[kOpp1].y : s.p[kOpp2].y;
+    }
+    const double d1x = right ? s.p[kAI1].x : s.p[kOpp1].x, d1y = right ? s.p[kAI1].y : s.p[kOpp1].y;
+    const double d2x = right ? s.p[kAI2].x : s.p[kOpp2].x, d2y = right ? s.p[kAI2].y : s.p[kOpp2].y;
+    // bigger_than(d1, d2, 2), :76-82 = how many of the two defenders are within 2.0
+    const int near = (sqsum(dsub(d1x, px), dsub(d1y, py)) <= kSqLe2 ? 1 : 0) +
+                     (sqsum(dsub(d2x, px), dsub(d2y, py)) <= kSqLe2 ? 1 : 0);
+    const double accuracy = dadd(10.0, dmul((double)near, 20.0));        // :364
+    const double vx = dsub(right ? 0.0 : kFieldLen, s.b.x), vy = dsub((double)shot.target_y, s.b.y);   // :373-376
+    const double mag = hyp(vx, vy);
+
+    const uint32_t pick = __umulhi(rng.word_at(shot.pick_idx), 10u);     // randint(0, 9), :107
+    const Philox4 nb = philox_step_block(rng.seed, rng.env_id, rng.stream, rng.t, kNormalBlock0 + (pick >> 1));
     const uint32_t w0 = (pick & 1u) ? nb.z : nb.x, w1 = (pick & 1u) ? nb.w : nb.y;
     const double u1 = (double)((w0 >> 8) + 1u) * (1.0 / 16777216.0);
     const double u2 = (double)(w1 >> 8) * (1.0 / 16777216.0);
     double bm_sin, bm_cos;
     fm_sincos(dmul(6.283185307179586, u2), bm_sin, bm_cos);
     const double z = dmul(__dsqrt_rn(dmul(-2.0, fm_log(u1))), bm_cos);
-    const double nd = dadd(0.0, dmul(accuracy, z));                      // np.random.normal(0, accuracy)
+    const double nd = dadd(0.0, dmul(accuracy, z));                      // np.random.normal(0, accuracy), :103
     const double c = ddiv(dmul(vx, 1.0), mag), sn = ddiv(dmul(vy, 1.0), mag);  // :105-106
     const double swing = dmul(ddiv(nd, 180.0), 3.141592653589793);       // :108
     double ss, sc;
     fm_sincos(swing, ss, sc);                                            // :109-110
     const double tc = dsub(dmul(c, sc), dmul(sn, ss));                   // :113
     const double ts = dadd(dmul(sn, sc), dmul(c, ss));                   // :114
-    ox = dmul(tc, mag);                                                  // :115
-    oy = dmul(ts, mag);
-}
-
-// intercept_chance(d, 1, 2), :122-129
-__device__ __forceinline__ double intercept_chance(double d)
-{
-    if (d < 1.0) return 0.9;
-    if (d <= 2.0) return dmul(ddiv(0.9, dsub(1.0, 2.0)), dsub(d, 2.0));
-    return 0.0;
-}
-
-// _set_vector_observation, :300-530, for one player.
-template <int AGENT>
-__device__ __forceinline__ void set_vector_observation(V0State &s, V0Rng &rng, const V0Params &P, bool has_ball,
-                                                       int action, bool set_target, double tgx, double tgy)
-{
-    constexpr bool right = AGENT >= kOpp1;
-    constexpr double goal_x = right ? 0.0 : kFieldLen;
-    Row &ao = s.p[AGENT];
-    const double target_y = (double)rng.randint(32, 36);                 // :306 -- always drawn first
-
-    if (has_ball) {
-        if (action == kIntercept) {                                      // :318-321
-            zero_motion(ao);
-            zero_motion(s.b);
-        } else if (action == kRun) {                                     // :330-356
-            ao.sp = P.player_speed;
-            if (set_target) { ao.tx = tgx; ao.ty = tgy; }
-            else { ao.tx = dsub(goal_x, ao.x); ao.ty = dsub(target_y, ao.y); }
-            if (rng.random() < 0.05) s.owner = kNoOne;                   // :353-354 (Q3)
-            else s.b = ao;                                               // :356
-        } else if (action == kShoot) {                                   // :362-383
-            const double accuracy = dadd(10.0, dmul((double)defence_near<AGENT>(s, P), 20.0));  // :364
-            s.b.sp = (double)rng.randint(P.shoot_speed - 16, P.shoot_speed);                      // :367
-            const double vx = dsub(goal_x, s.b.x), vy = dsub(target_y, s.b.y);
-            screw_vec(rng, vx, vy, hyp(vx, vy), accuracy, s.b.tx, s.b.ty);                        // :373-378
-            s.last_owner = s.owner;                                      // :381
-            s.owner = kNoOne;                                            // :382
-            zero_motion(ao);                                             // :383
-        } else {                                                         // assist, :385-423
-            const Row &mate = s.p[AGENT ^ 1];
-            const double vx = dsub(mate.x, s.b.x), vy = dsub(mate.y, s.b.y);   // :412
-            double sp = ddiv(hyp(vx, vy), kStepSize);                    // :413
-            if (sp > 20.0) sp = 20.0;                                    // :414-415
-            const double lo = dsub(sp, 1.0), hi = dadd(sp, 1.0);
-            s.b.sp = dadd(lo, dmul(dsub(hi, lo), rng.random()));         // random.uniform, :416
-            s.b.tx = vx; s.b.ty = vy;                                    // :418
-            s.last_owner = s.owner;                                      // :421
-            s.owner = kNoOne;                                            // :422
-            zero_motion(ao);                                             // :423
-        }
-    } else {
-        const double bx = dsub(s.b.x, ao.x), by = dsub(s.b.y, ao.y);     // :432
-        if (action == kIntercept) {                                      // :452-476 (Q4: player keeps moving)
-            const double mag = hyp(bx, by);
-            const bool success = rng.random() < intercept_chance(mag);   // :459 -- drawn even when far
-            if (success || (s.owner == kNoOne && mag < 4.0)) {           // :462-463
-                s.b = ao;                                                // :465-466
-                s.last_owner = s.owner;                                  // :467
-                s.owner = AGENT;                                         // :468
-            }
-        } else if (action == kRun) {                                     // :483-503
-            ao.sp = P.player_speed;
-            if (set_target) { ao.tx = tgx; ao.ty = tgy; }
-            else if (s.owner != AGENT) { ao.tx = bx; ao.ty = by; }       // :501
-            else { ao.tx = dsub(goal_x, ao.x); ao.ty = dsub(kFieldWid / 2, ao.y); }  // :503 (dead, Q12)
-        } else {                                                         // shoot / assist without the ball, :509-525
-            zero_motion(ao);
-        }
-    }
+    s.b.tx = dmul(tc, mag);                                              // :115
+    s.b.ty = dmul(ts, mag);
 }
 
 // Easy_Agent.get_action_type for a 'right' opponent, easy_agent.py:53-98
@@ -239,63 +261,63 @@ __device__ __forceinline__ int easy_action(const V0State &s, V0Rng &rng, bool ha
 {
     const Row &ao = s.p[AGENT];
     const Row &mo = s.p[AGENT ^ 1];
-    if (has_ball) {
-        if (ao.x <= 20.0) return kShoot;                                 // :77-79, shoot_x = 0 + 20
-        if (mo.x < ao.x || mo.y < dsub(ao.y, 7.0) || mo.y > dadd(ao.y, 7.0)) {   // :81-83 (short-circuit order)
-            if (rng.random() > 0.8 && hyp(dsub(mo.x, ao.x), dsub(mo.y, ao.y)) > 12.0) return kAssist;
-        }
-        return kRun;
-    }
-    if (!team_has_ball && hyp(dsub(s.b.x, ao.x), dsub(s.b.y, ao.y)) <= 1.0) return kIntercept;  // :90-92
-    return kRun;
+    const bool in_range = ao.x <= 20.0;                                  // :77-79, shoot_x = 0 + 20
+    const bool open_mate = mo.x < ao.x || mo.y < dsub(ao.y, 7.0) || mo.y > dadd(ao.y, 7.0);   // :81-83
+    // the draw happens only when the geometric clause holds (short-circuit `and`, :81-85)
+    const uint32_t w = rng.take_if(has_ball && !in_range && open_mate);
+    const bool lucky = (double)(w >> 8) * (1.0 / 16777216.0) > 0.8;
+    const bool far_mate = sqsum(dsub(mo.x, ao.x), dsub(mo.y, ao.y)) > kSqGt12;                // distance > 12
+    const bool ball_close = sqsum(dsub(s.b.x, ao.x), dsub(s.b.y, ao.y)) <= kSqLe1;           // distance <= 1.0, :90
+    const int with_ball = in_range ? (int)kShoot : ((open_mate && lucky && far_mate) ? (int)kAssist : (int)kRun);
+    const int without = (!team_has_ball && ball_close) ? (int)kIntercept : (int)kRun;         // :90-96
+    return has_ball ? with_ball : without;
 }
 
 // _step_by_observation, :560-571 (DECELERATION = 0: the ball's speed update is `sp -= 0.0`)
 __device__ __forceinline__ void advance(Row &o)
 {
-    const double mag = hyp(o.tx, o.ty);                                  // :562
-    if (mag != 0.0) {
+    const double s2 = sqsum(o.tx, o.ty);                                 // :562; sqrt(s2) == 0 <=> s2 == 0
+    if (s2 != 0.0) {
+        const double mag = __dsqrt_rn(s2);
         o.x = dadd(o.x, dmul(o.sp, ddiv(dmul(o.tx, kStepSize), mag)));   // :567
         o.y = dadd(o.y, dmul(o.sp, ddiv(dmul(o.ty, kStepSize), mag)));   // :568
     }
 }
 
 // _opp_team_set_vector_observation, :864-982
-__device__ __forceinline__ void opp_team(V0State &s, V0Rng &rng, const V0Params &P)
+__device__ __forceinline__ void opp_team(V0State &s, V0Rng &rng, const V0Params &P, PendingShot &shot)
 {
-    const bool has1 = s.owner == kOpp1, has2 = s.owner == kOpp2;         // :866-877
+    const bool has1 = s.owner == kOpp1, has2 = s.owner == kOpp2;         // :866-877 (latched before either acts)
     const bool team_has = has1 || has2;
     const int a1 = easy_action<kOpp1>(s, rng, has1, team_has);           // :879
     const int a2 = easy_action<kOpp2>(s, rng, has2, team_has);           // :880
+    const bool run1 = a1 == kRun, run2 = a2 == kRun;
     int a1_type = a1, a2_type = a2;                                      // overrides do not touch a1 / a2
-    bool set1 = false, set2 = false;
-    double t1x = 0, t1y = 0, t2x = 0, t2y = 0;
     const Row &o1 = s.p[kOpp1], &o2 = s.p[kOpp2];
-    const bool diag1 = o1.y > dmul(kFieldWid, 0.2), diag2 = o2.y < dmul(kFieldWid, 0.8);
-    if (has1 && a1 == kRun) {                                            // :893-909
-        if (diag1) { set1 = true; t1x = -1; t1y = -1; }
-        if (a2 == kRun && o2.x > dmul(kFieldLen, 0.1) && diag2) { set2 = true; t2x = -1; t2y = 1; }
-    }
-    if (has2 && a2 == kRun) {                                            // :911-928
-        if (diag2) { set2 = true; t2x = -1; t2y = 1; }
-        if (a1 == kRun && o1.x > dmul(kFieldLen, 0.1) && diag1) { set1 = true; t1x = -1; t1y = -1; }
-    }
-    if ((s.owner == kAI1 || s.owner == kAI2) && s.b.x < dmul(kFieldLen, 0.6)) {   // :931-947
-        const double dpx = dmul(kFieldLen, 0.75), dpy = dmul(kFieldWid, 0.5);
+    const bool diag1 = o1.y > kWid02, diag2 = o2.y < kWid08;
+    // carrier runs on the diagonal, its running mate mirrors it, :893-928
+    bool set1 = diag1 && ((has1 && run1) || (has2 && run2 && run1 && o1.x > kLen01));
+    bool set2 = diag2 && ((has2 && run2) || (has1 && run1 && run2 && o2.x > kLen01));
+    double t1x = -1.0, t1y = -1.0, t2x = -1.0, t2y = 1.0;
+    if ((s.owner == kAI1 || s.owner == kAI2) && s.b.x < kLen06) {   // :931-947: the deeper opp defends
+        const double dpx = kDefendX, dpy = kDefendY;
         if (o1.x > o2.x) { a1_type = kRun; set1 = true; t1x = dsub(dpx, o1.x); t1y = dsub(dpy, o1.y); }
         else             { a2_type = kRun; set2 = true; t2x = dsub(dpx, o2.x); t2y = dsub(dpy, o2.y); }
     }
-    set_vector_observation<kOpp1>(s, rng, P, has1, a1_type, set1, t1x, t1y);   // :951-954
-    set_vector_observation<kOpp2>(s, rng, P, has2, a2_type, set2, t2x, t2y);   // :956-959
-    if (s.owner == kNoOne && a1 == kRun && a2 == kRun) {                 // :962-982 anticipate the ball
+    player_turn<kOpp1>(s, rng, P, has1, a1_type, set1, t1x, t1y, shot);  // :951-954
+    player_turn<kOpp2>(s, rng, P, has2, a2_type, set2, t2x, t2y, shot);  // :956-959
+    {   // :962-982 anticipate the ball: whoever can reach its next position lands exactly on it
         Row nb = s.b;
         advance(nb);
         const double v1x = dsub(nb.x, s.p[kOpp1].x), v1y = dsub(nb.y, s.p[kOpp1].y);
         const double v2x = dsub(nb.x, s.p[kOpp2].x), v2y = dsub(nb.y, s.p[kOpp2].y);
-        const double m1 = hyp(v1x, v1y), m2 = hyp(v2x, v2y);
-        const double reach = dmul(kStepSize, P.player_speed);
-        if (m1 < reach) { s.p[kOpp1].tx = v1x; s.p[kOpp1].ty = v1y; s.p[kOpp1].sp = ddiv(m1, kStepSize); }
-        else if (m2 < reach) { s.p[kOpp2].tx = v2x; s.p[kOpp2].ty = v2y; s.p[kOpp2].sp = ddiv(m2, kStepSize); }
+        const double q1 = sqsum(v1x, v1y), q2 = sqsum(v2x, v2y);
+        const bool on = s.owner == kNoOne && run1 && run2;
+        const bool c1 = on && q1 <= P.reach_sq_max;                      // hyp(v1) < 0.1 * player_speed
+        const bool c2 = on && !c1 && q2 <= P.reach_sq_max;
+        const double sp = ddiv(__dsqrt_rn(c1 ? q1 : q2), kStepSize);
+        if (c1) { s.p[kOpp1].tx = v1x; s.p[kOpp1].ty = v1y; s.p[kOpp1].sp = sp; }
+        if (c2) { s.p[kOpp2].tx = v2x; s.p[kOpp2].ty = v2y; s.p[kOpp2].sp = sp; }
     }
 }
 
@@ -306,11 +328,17 @@ __device__ __forceinline__ bool player_out(const Row &o)
 
 struct StepResult { double reward; int done; int flags; };
 
-// FutbolEnv.step, :628-717.  `ai_action` in 0..15.
-__device__ __forceinline__ StepResult v0_step(V0State &s, const V0Params &P, uint32_t env_id, int ai_action)
+// FutbolEnv.step, :628-717.  `ai_action` in 0..15.  `rng_col`: this thread's column of the shared-memory
+// draw buffer (StepRng).  RANDOM_OPP = the constructor's random_opp (:138), a compile-time variant so that each
+// kernel carries only its own opponent code.
+template <bool RANDOM_OPP>
+__device__ __forceinline__ StepResult v0_step(V0State &s, const V0Params &P, uint32_t env_id, int ai_action,
+                                              uint32_t *rng_col)
 {
     V0Rng rng;
-    rng.begin(P.seed, env_id, kStreamDynamics, s.t_total);
+    rng.begin(rng_col, P.seed, env_id, kStreamDynamics, s.t_total);
+    PendingShot shot;
+    shot.shooter = -1; shot.target_y = 0; shot.pick_idx = 0;
 
     // pre-step snapshot used by the reward (:630-635).  The owner one-hot row of the observation is all
     // zeros between reset() and the end of the first step, otherwise 10 * onehot(owner).
@@ -320,16 +348,17 @@ __device__ __forceinline__ StepResult v0_step(V0State &s, const V0Params &P, uin
     const bool pre_ai1 = !fresh && s.owner == kAI1, pre_ai2 = !fresh && s.owner == kAI2;
     const bool pre_none = !fresh && s.owner == kNoOne;
 
-    if (P.random_opp) {                                                  // :639-645
-        const int r = rng.randint(0, 15);
-        set_vector_observation<kOpp1>(s, rng, P, s.owner == kOpp1, r >> 2, false, 0, 0);
-        set_vector_observation<kOpp2>(s, rng, P, s.owner == kOpp2, r & 3, false, 0, 0);
+    if (RANDOM_OPP) {                                                    // :639-645
+        const int r = (int)__umulhi(rng.take(), 16u);                    // randint(0, 15)
+        player_turn<kOpp1>(s, rng, P, s.owner == kOpp1, r >> 2, false, 0, 0, shot);
+        player_turn<kOpp2>(s, rng, P, s.owner == kOpp2, r & 3, false, 0, 0, shot);
     } else {
-        opp_team(s, rng, P);                                             // :649
+        opp_team(s, rng, P, shot);                                       // :649
     }
     const int action1 = ai_action >> 2, action2 = ai_action & 3;         // :653
-    set_vector_observation<kAI1>(s, rng, P, s.owner == kAI1, action1, false, 0, 0);   // :655
-    set_vector_observation<kAI2>(s, rng, P, s.owner == kAI2, action2, false, 0, 0);   // :656
+    player_turn<kAI1>(s, rng, P, s.owner == kAI1, action1, false, 0, 0, shot);   // :655
+    player_turn<kAI2>(s, rng, P, s.owner == kAI2, action2, false, 0, 0, shot);   // :656
+    if (shot.shooter >= 0) resolve_shot(s, rng, P, shot);
 
 #pragma unroll
     for (int i = 0; i < 4; ++i) advance(s.p[i]);                         // :661
@@ -344,22 +373,22 @@ __device__ __forceinline__ StepResult v0_step(V0State &s, const V0Params &P, uin
         if (P.only_reward_goal) {
             reward = dadd(score, get_scored);                            // :857-858
         } else {
-            const double d1 = hyp(dsub(ob_x, o1_x), dsub(ob_y, o1_y));   // :757
-            const double d2 = hyp(dsub(ob_x, o2_x), dsub(ob_y, o2_y));   // :758
+            const bool far1 = sqsum(dsub(ob_x, o1_x), dsub(ob_y, o1_y)) > kSqLe2;   // distance > 2, :757, :790
+            const bool far2 = sqsum(dsub(ob_x, o2_x), dsub(ob_y, o2_y)) > kSqLe2;   // :758, :799
             const double running_r = (action1 == kRun || action2 == kRun) ? 2.0 : 0.0;       // :772-775
             const double adv_r = ((pre_ai1 && action2 == kRun) || (pre_ai2 && action1 == kRun)) ? 2.0 : 0.0;  // :777-781
             double bad1, bad2;
-            if (!pre_ai1) bad1 = (action1 == kAssist || action1 == kShoot) ? -1.0 : ((d1 > 2.0 && action1 == kIntercept) ? -0.5 : 0.0);
+            if (!pre_ai1) bad1 = (action1 == kAssist || action1 == kShoot) ? -1.0 : ((far1 && action1 == kIntercept) ? -0.5 : 0.0);
             else bad1 = action1 == kIntercept ? -1.0 : 0.0;              // :783-794
-            if (!pre_ai2) bad2 = (action2 == kAssist || action2 == kShoot) ? -1.0 : ((d2 > 2.0 && action1 == kIntercept) ? -0.5 : 0.0);  // Q5
+            if (!pre_ai2) bad2 = (action2 == kAssist || action2 == kShoot) ? -1.0 : ((far2 && action1 == kIntercept) ? -0.5 : 0.0);  // Q5
             else bad2 = action2 == kIntercept ? -1.0 : 0.0;              // :796-807
             const double out_r = (player_out(s.p[kAI1]) || player_out(s.p[kAI2])) ? -0.6 : 0.0;   // :823-826
             const bool ai_owns = s.owner == kAI1 || s.owner == kAI2;
             double get_ball;
             if (ai_owns && !pre_ai1 && !pre_ai2)                          // :828-836 (Q6)
-                get_ball = (ob_tx > ob_ty && ob_tx > 0.0 && ob_x > o1_x && ob_x > o2_x && pre_none) ? dmul(-50.0, 0.3) : dmul(60.0, 0.3);
+                get_ball = (ob_tx > ob_ty && ob_tx > 0.0 && ob_x > o1_x && ob_x > o2_x && pre_none) ? kRewStolen : kRewGained;
             else if ((s.owner == kAI1 && pre_ai1) || (s.owner == kAI2 && pre_ai2))
-                get_ball = dmul(30.0, 0.3);                              // :837-839
+                get_ball = kRewKept;                                 // :837-839
             else
                 get_ball = 0.0;
             reward = dadd(dadd(dadd(dadd(dadd(dadd(get_ball, score), get_scored), out_r), dadd(bad1, bad2)), adv_r), running_r);  // :861
