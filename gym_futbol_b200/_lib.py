@@ -60,7 +60,12 @@ def load():
     if _lib is not None:
         return _lib
     path = lib_path()
-    if _build.is_stale():
+    variant = os.environ.get("FUTBOL_B200_LIB")     # tuning aid: an alternative build of the same sources (tools/)
+    if variant:
+        path = variant if os.path.isabs(variant) else os.path.join(os.path.dirname(path), variant)
+        if not os.path.exists(path):
+            raise FutbolError("FUTBOL_B200_LIB=%s does not exist" % path)
+    elif _build.is_stale():
         try:
             _build.build_extension()
         except Exception as exc:  # no nvcc on this box and no prebuilt library

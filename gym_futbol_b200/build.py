@@ -37,16 +37,18 @@ def is_stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build_extension(force=False, verbose=False):
-    if not force and not is_stale():
+def build_extension(force=False, verbose=False, extra_flags=(), out=None):
+    """`extra_flags` / `out`: tuning variants (e.g. -DFUTBOL_MIN_BLOCKS=4 into libfutbol_b200_mb4.so)."""
+    if out is None and not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + list(SOURCES)
+    out = LIB if out is None else os.path.join(CSRC, out)
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + list(SOURCES)
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
     if verbose:
         sys.stderr.write(proc.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -74,6 +74,7 @@ int futbol_create(const FutbolConfig *cfg, FutbolHandle **out)
     h->initialised = false;
     V0Params &P = h->v0;
     P.seed = cfg->seed;
+    P.key = philox_expand_key(cfg->seed);
     P.env_id_offset = cfg->env_id_offset;
     P.n_envs = cfg->n_envs;
     P.random_opp = cfg->random_opp != 0;

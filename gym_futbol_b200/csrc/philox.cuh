@@ -22,35 +22,45 @@ constexpr int kPreDraws = 8;              // draws generated up front per step (
 
 struct Philox4 { uint32_t x, y, z, w; };
 
-__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                 uint32_t k0, uint32_t k1)
+// The ten round keys of a seed (k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85).  The seed is the same for every
+// environment, so the host expands it once and the keys reach the kernel as launch constants: a round is
+// two 32x32->64 multiplies and two three-input XORs.
+struct PhiloxKey { uint32_t k0[10], k1[10]; };
+
+__host__ __device__ inline PhiloxKey philox_expand_key(uint64_t seed)
+{
+    PhiloxKey K;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { K.k0[r] = k0; K.k1[r] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return K;
+}
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey &K)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0;
-        c2 = hi0 ^ c3 ^ k1;
+        c0 = hi1 ^ c1 ^ K.k0[r];
+        c2 = hi0 ^ c3 ^ K.k1[r];
         c1 = lo1;
         c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
     }
     return Philox4{c0, c1, c2, c3};
 }
 
-__device__ __forceinline__ Philox4 philox_step_block(uint64_t seed, uint32_t env_id, uint32_t stream,
+__device__ __forceinline__ Philox4 philox_step_block(const PhiloxKey &K, uint32_t env_id, uint32_t stream,
                                                      uint64_t t, uint32_t block)
 {
-    return philox4x32_10((uint32_t)t, ((uint32_t)(t >> 32) & 0xFFFFu) | (block << 16), env_id, stream,
-                         (uint32_t)seed, (uint32_t)(seed >> 32));
+    return philox4x32_10((uint32_t)t, ((uint32_t)(t >> 32) & 0xFFFFu) | (block << 16), env_id, stream, K);
 }
 
 // draws past the pre-generated ones: out of line, a step needs at most 10 and almost always <= 8
 static __device__ __noinline__ uint32_t philox_step_word(uint64_t seed, uint32_t env_id, uint32_t stream, uint64_t t,
                                                          uint32_t idx)
 {
-    const Philox4 p = philox_step_block(seed, env_id, stream, t, idx >> 2);
+    const PhiloxKey K = philox_expand_key(seed);
+    const Philox4 p = philox_step_block(K, env_id, stream, t, idx >> 2);
     const uint32_t lo = (idx & 1u) ? p.y : p.x, hi = (idx & 1u) ? p.w : p.z;
     return (idx & 2u) ? hi : lo;
 }
@@ -62,15 +72,18 @@ static __device__ __noinline__ uint32_t philox_step_word(uint64_t seed, uint32_t
 // buf[k * kEnvThreads + tid]: every lane hits its own bank whatever its j), and a draw is one LDS.
 struct StepRng {
     const uint32_t *col;
-    uint64_t seed, t;
+    const PhiloxKey *key;
+    uint64_t t;
     uint32_t env_id, stream, j;
 
-    __device__ __forceinline__ void begin(uint32_t *col_, uint64_t seed_, uint32_t env_id_, uint32_t stream_, uint64_t t_)
+    __device__ __forceinline__ uint64_t seed() const { return (uint64_t)key->k0[0] | ((uint64_t)key->k1[0] << 32); }
+
+    __device__ __forceinline__ void begin(uint32_t *col_, const PhiloxKey &key_, uint32_t env_id_, uint32_t stream_, uint64_t t_)
     {
-        col = col_; seed = seed_; env_id = env_id_; stream = stream_; t = t_; j = 0;
+        col = col_; key = &key_; env_id = env_id_; stream = stream_; t = t_; j = 0;
 #pragma unroll
         for (int b = 0; b < kPreDraws / 4; ++b) {
-            const Philox4 p = philox_step_block(seed, env_id, stream, t, b);
+            const Philox4 p = philox_step_block(*key, env_id, stream, t, b);
             col_[(4 * b + 0) * kEnvThreads] = p.x; col_[(4 * b + 1) * kEnvThreads] = p.y;
             col_[(4 * b + 2) * kEnvThreads] = p.z; col_[(4 * b + 3) * kEnvThreads] = p.w;
         }
@@ -79,7 +92,7 @@ struct StepRng {
     __device__ __forceinline__ uint32_t word_at(uint32_t idx) const
     {
         if (idx < (uint32_t)kPreDraws) return col[idx * kEnvThreads];
-        return philox_step_word(seed, env_id, stream, t, idx);
+        return philox_step_word(seed(), env_id, stream, t, idx);
     }
 
     __device__ __forceinline__ uint32_t take() { return word_at(j++); }
@@ -88,7 +101,7 @@ struct StepRng {
     {
         uint32_t w = 0;
         if (j < (uint32_t)kPreDraws) w = col[j * kEnvThreads];
-        else if (c) w = philox_step_word(seed, env_id, stream, t, j);
+        else if (c) w = philox_step_word(seed(), env_id, stream, t, j);
         j += c ? 1u : 0u;
         return w;
     }
@@ -96,9 +109,9 @@ struct StepRng {
 
 typedef StepRng V0Rng;
 
-__device__ __forceinline__ int philox_action(uint64_t seed, uint32_t env_id, uint64_t t, uint32_t n_actions)
+__device__ __forceinline__ int philox_action(const PhiloxKey &K, uint32_t env_id, uint64_t t, uint32_t n_actions)
 {
-    return (int)__umulhi(philox_step_block(seed, env_id, kStreamActions, t, 0).x, n_actions);
+    return (int)__umulhi(philox_step_block(K, env_id, kStreamActions, t, 0).x, n_actions);
 }
 
 }  // namespace futbol

@@ -137,9 +137,12 @@ __global__ void __launch_bounds__(kEnvThreads) v0_step_kernel(V0Params P, StateV
 
 // ---- fused K-step rollout ----------------------------------------------------------------------------
 constexpr int kRolloutThreads = kEnvThreads;
+#ifndef FUTBOL_MIN_BLOCKS
+#define FUTBOL_MIN_BLOCKS 4     // resident blocks per SM the register allocation is sized for
+#endif
 
 template <bool RANDOM_OPP>
-__global__ void __launch_bounds__(kRolloutThreads)
+__global__ void __launch_bounds__(kRolloutThreads, FUTBOL_MIN_BLOCKS)
 v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ actions, float *__restrict__ obs,
                   float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
 {
@@ -168,7 +171,7 @@ v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ ac
         const size_t slot = (size_t)k * n + (size_t)i;
         int a;
         if (actions != nullptr) a = live ? (__ldg(actions + slot) & 15) : 0;
-        else a = philox_action(P.seed, env_id, s.t_total, 16);
+        else a = philox_action(P.key, env_id, s.t_total, 16);
         const int ai_before = s.ai_score;
         const StepResult r = v0_step<RANDOM_OPP>(s, P, env_id, a, draws + threadIdx.x);
         last_flags = r.flags;

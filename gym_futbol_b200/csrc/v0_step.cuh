@@ -55,6 +55,7 @@ struct Row { double x, y, tx, ty, sp; };
 
 struct V0Params {
     uint64_t seed;
+    PhiloxKey key;       // philox_expand_key(seed), set by the host
     uint32_t env_id_offset;
     int n_envs;
     int random_opp, one_goal_end, only_reward_goal, auto_reset;
@@ -177,10 +178,19 @@ __device__ __forceinline__ void player_turn(V0State &s, V0Rng &rng, const V0Para
     const double bx = dsub(s.b.x, ao.x), by = dsub(s.b.y, ao.y);         // :432
     const double vx = hb_assist ? dsub(mate.x, s.b.x) : bx;              // :412
     const double vy = hb_assist ? dsub(mate.y, s.b.y) : by;
-    const double mag = hyp(vx, vy);                                      // the one magnitude a turn needs
+    // The one magnitude a turn needs (no-ball intercept: |ball - player|; has-ball assist: |mate - ball|).
+    // sqrt(0) and 0/x leave the fast path of the IEEE sequences (a subroutine call for the lanes that
+    // hold the ball, whose ball-player vector is exactly zero), so those lanes are fed a benign operand
+    // and the exact result (0) is selected afterwards.
+    const double q = sqsum(vx, vy);
+    const bool q_zero = q == 0.0;
+    const bool need_mag = nb_int || hb_assist;
+    const double root = __dsqrt_rn((need_mag && !q_zero) ? q : 1.0);
+    const double mag = q_zero ? 0.0 : root;
 
     // has-ball assist, :413-416
-    double pass = ddiv(mag, kStepSize);
+    const double quot = ddiv((hb_assist && !q_zero) ? mag : 1.0, kStepSize);
+    double pass = q_zero ? 0.0 : quot;
     pass = pass > 20.0 ? 20.0 : pass;
     const double lo = dsub(pass, 1.0), hi = dadd(pass, 1.0);
     const double pass_speed = dadd(lo, dmul(dsub(hi, lo), u));           // random.uniform
@@ -237,7 +247,7 @@ __device__ __forceinline__ void resolve_shot(V0State &s, const V0Rng &rng, const
     const double mag = hyp(vx, vy);
 
     const uint32_t pick = __umulhi(rng.word_at(shot.pick_idx), 10u);     // randint(0, 9), :107
-    const Philox4 nb = philox_step_block(rng.seed, rng.env_id, rng.stream, rng.t, kNormalBlock0 + (pick >> 1));
+    const Philox4 nb = philox_step_block(P.key, rng.env_id, rng.stream, rng.t, kNormalBlock0 + (pick >> 1));
     const uint32_t w0 = (pick & 1u) ? nb.z : nb.x, w1 = (pick & 1u) ? nb.w : nb.y;
     const double u1 = (double)((w0 >> 8) + 1u) * (1.0 / 16777216.0);
     const double u2 = (double)(w1 >> 8) * (1.0 / 16777216.0);
@@ -273,14 +283,17 @@ __device__ __forceinline__ int easy_action(const V0State &s, V0Rng &rng, bool ha
     return has_ball ? with_ball : without;
 }
 
-// _step_by_observation, :560-571 (DECELERATION = 0: the ball's speed update is `sp -= 0.0`)
+// _step_by_observation, :560-571 (DECELERATION = 0: the ball's speed update is `sp -= 0.0`).
+// A zero component (0 / mag = that same signed zero) is kept off the divider's slow path.
 __device__ __forceinline__ void advance(Row &o)
 {
     const double s2 = sqsum(o.tx, o.ty);                                 // :562; sqrt(s2) == 0 <=> s2 == 0
     if (s2 != 0.0) {
         const double mag = __dsqrt_rn(s2);
-        o.x = dadd(o.x, dmul(o.sp, ddiv(dmul(o.tx, kStepSize), mag)));   // :567
-        o.y = dadd(o.y, dmul(o.sp, ddiv(dmul(o.ty, kStepSize), mag)));   // :568
+        const double nx = dmul(o.tx, kStepSize), ny = dmul(o.ty, kStepSize);
+        const double qx = ddiv(nx == 0.0 ? mag : nx, mag), qy = ddiv(ny == 0.0 ? mag : ny, mag);
+        o.x = dadd(o.x, dmul(o.sp, nx == 0.0 ? nx : qx));                // :567
+        o.y = dadd(o.y, dmul(o.sp, ny == 0.0 ? ny : qy));                // :568
     }
 }
 
@@ -315,7 +328,10 @@ __device__ __forceinline__ void opp_team(V0State &s, V0Rng &rng, const V0Params 
         const bool on = s.owner == kNoOne && run1 && run2;
         const bool c1 = on && q1 <= P.reach_sq_max;                      // hyp(v1) < 0.1 * player_speed
         const bool c2 = on && !c1 && q2 <= P.reach_sq_max;
-        const double sp = ddiv(__dsqrt_rn(c1 ? q1 : q2), kStepSize);
+        const double qs = c1 ? q1 : q2;
+        const bool live = (c1 || c2) && qs != 0.0;                       // others: benign operand, result unused
+        const double ms = __dsqrt_rn(live ? qs : 1.0);
+        const double sp = qs == 0.0 ? 0.0 : ddiv(live ? ms : 1.0, kStepSize);
         if (c1) { s.p[kOpp1].tx = v1x; s.p[kOpp1].ty = v1y; s.p[kOpp1].sp = sp; }
         if (c2) { s.p[kOpp2].tx = v2x; s.p[kOpp2].ty = v2y; s.p[kOpp2].sp = sp; }
     }
@@ -336,17 +352,19 @@ __device__ __forceinline__ StepResult v0_step(V0State &s, const V0Params &P, uin
                                               uint32_t *rng_col)
 {
     V0Rng rng;
-    rng.begin(rng_col, P.seed, env_id, kStreamDynamics, s.t_total);
+    rng.begin(rng_col, P.key, env_id, kStreamDynamics, s.t_total);
     PendingShot shot;
     shot.shooter = -1; shot.target_y = 0; shot.pick_idx = 0;
 
     // pre-step snapshot used by the reward (:630-635).  The owner one-hot row of the observation is all
     // zeros between reset() and the end of the first step, otherwise 10 * onehot(owner).
     const bool fresh = s.ep_step == 0;
-    const double ob_x = s.b.x, ob_tx = s.b.tx, ob_ty = s.b.ty, ob_y = s.b.y;
-    const double o1_x = s.p[kAI1].x, o1_y = s.p[kAI1].y, o2_x = s.p[kAI2].x, o2_y = s.p[kAI2].y;
     const bool pre_ai1 = !fresh && s.owner == kAI1, pre_ai2 = !fresh && s.owner == kAI2;
     const bool pre_none = !fresh && s.owner == kNoOne;
+    // everything _get_reward reads from the snapshot is a comparison of pre-step values: evaluate them now
+    const bool far1 = sqsum(dsub(s.b.x, s.p[kAI1].x), dsub(s.b.y, s.p[kAI1].y)) > kSqLe2;   // distance > 2, :757, :790
+    const bool far2 = sqsum(dsub(s.b.x, s.p[kAI2].x), dsub(s.b.y, s.p[kAI2].y)) > kSqLe2;   // :758, :799
+    const bool own_forward_pass = s.b.tx > s.b.ty && s.b.tx > 0.0 && s.b.x > s.p[kAI1].x && s.b.x > s.p[kAI2].x && pre_none;  // :831 (Q6)
 
     if (RANDOM_OPP) {                                                    // :639-645
         const int r = (int)__umulhi(rng.take(), 16u);                    // randint(0, 15)
@@ -373,8 +391,6 @@ __device__ __forceinline__ StepResult v0_step(V0State &s, const V0Params &P, uin
         if (P.only_reward_goal) {
             reward = dadd(score, get_scored);                            // :857-858
         } else {
-            const bool far1 = sqsum(dsub(ob_x, o1_x), dsub(ob_y, o1_y)) > kSqLe2;   // distance > 2, :757, :790
-            const bool far2 = sqsum(dsub(ob_x, o2_x), dsub(ob_y, o2_y)) > kSqLe2;   // :758, :799
             const double running_r = (action1 == kRun || action2 == kRun) ? 2.0 : 0.0;       // :772-775
             const double adv_r = ((pre_ai1 && action2 == kRun) || (pre_ai2 && action1 == kRun)) ? 2.0 : 0.0;  // :777-781
             double bad1, bad2;
@@ -386,7 +402,7 @@ __device__ __forceinline__ StepResult v0_step(V0State &s, const V0Params &P, uin
             const bool ai_owns = s.owner == kAI1 || s.owner == kAI2;
             double get_ball;
             if (ai_owns && !pre_ai1 && !pre_ai2)                          // :828-836 (Q6)
-                get_ball = (ob_tx > ob_ty && ob_tx > 0.0 && ob_x > o1_x && ob_x > o2_x && pre_none) ? kRewStolen : kRewGained;
+                get_ball = own_forward_pass ? kRewStolen : kRewGained;
             else if ((s.owner == kAI1 && pre_ai1) || (s.owner == kAI2 && pre_ai2))
                 get_ball = kRewKept;                                 // :837-839
             else

@@ -33,7 +33,7 @@ void host_v0_rollout(uint64_t seed, uint32_t env_id0, int random_opp, int one_go
                      double *obs, double *reward, uint8_t *done, uint8_t *flags)
 {
     V0Params P;
-    P.seed = seed; P.env_id_offset = env_id0; P.n_envs = n; P.random_opp = random_opp; P.one_goal_end = one_goal_end;
+    P.seed = seed; P.key = philox_expand_key(seed); P.env_id_offset = env_id0; P.n_envs = n; P.random_opp = random_opp; P.one_goal_end = one_goal_end;
     P.only_reward_goal = only_reward_goal; P.auto_reset = auto_reset; P.ep_limit = ep_limit; P.shoot_speed = shoot_speed;
     P.player_speed = player_speed; P.reach_sq_max = reach_sq_max;
     uint32_t draws[kPreDraws];
