@@ -76,6 +76,20 @@ __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a,
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+// c ? a : b that the optimiser cannot look through.  Used where a lane is handed a benign operand to keep
+// it on the fast path of the IEEE sqrt/div sequence: with a plain ternary the compiler rewrites
+// sqrt(c ? q : 1.0) into c ? sqrt(q) : 1.0 and the zero operand is back (seen in ncu as 1-6 lanes per warp
+// inside __cuda_sm20_dsqrt_rn_f64_mediumpath / div_rn_f64_full on every step).
+#ifndef FUTBOL_HOST_SHIM
+__device__ __forceinline__ double pick(bool c, double a, double b)
+{
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b), "r"((int)c));
+    return r;
+}
+#else
+inline double pick(bool c, double a, double b) { return c ? a : b; }
+#endif
 __device__ __forceinline__ double sqsum(double vx, double vy) { return dadd(dmul(vx, vx), dmul(vy, vy)); }
 __device__ __forceinline__ double hyp(double vx, double vy) { return __dsqrt_rn(sqsum(vx, vy)); }   // get_vec, :62-65
 
@@ -185,11 +199,11 @@ __device__ __forceinline__ void player_turn(V0State &s, V0Rng &rng, const V0Para
     const double q = sqsum(vx, vy);
     const bool q_zero = q == 0.0;
     const bool need_mag = nb_int || hb_assist;
-    const double root = __dsqrt_rn((need_mag && !q_zero) ? q : 1.0);
+    const double root = __dsqrt_rn(pick(need_mag && !q_zero, q, 1.0));
     const double mag = q_zero ? 0.0 : root;
 
     // has-ball assist, :413-416
-    const double quot = ddiv((hb_assist && !q_zero) ? mag : 1.0, kStepSize);
+    const double quot = ddiv(pick(hb_assist && !q_zero, mag, 1.0), kStepSize);
     double pass = q_zero ? 0.0 : quot;
     pass = pass > 20.0 ? 20.0 : pass;
     const double lo = dsub(pass, 1.0), hi = dadd(pass, 1.0);
@@ -291,7 +305,7 @@ __device__ __forceinline__ void advance(Row &o)
     if (s2 != 0.0) {
         const double mag = __dsqrt_rn(s2);
         const double nx = dmul(o.tx, kStepSize), ny = dmul(o.ty, kStepSize);
-        const double qx = ddiv(nx == 0.0 ? mag : nx, mag), qy = ddiv(ny == 0.0 ? mag : ny, mag);
+        const double qx = ddiv(pick(nx == 0.0, mag, nx), mag), qy = ddiv(pick(ny == 0.0, mag, ny), mag);
         o.x = dadd(o.x, dmul(o.sp, nx == 0.0 ? nx : qx));                // :567
         o.y = dadd(o.y, dmul(o.sp, ny == 0.0 ? ny : qy));                // :568
     }
@@ -330,8 +344,8 @@ __device__ __forceinline__ void opp_team(V0State &s, V0Rng &rng, const V0Params 
         const bool c2 = on && !c1 && q2 <= P.reach_sq_max;
         const double qs = c1 ? q1 : q2;
         const bool live = (c1 || c2) && qs != 0.0;                       // others: benign operand, result unused
-        const double ms = __dsqrt_rn(live ? qs : 1.0);
-        const double sp = qs == 0.0 ? 0.0 : ddiv(live ? ms : 1.0, kStepSize);
+        const double ms = __dsqrt_rn(pick(live, qs, 1.0));
+        const double sp = qs == 0.0 ? 0.0 : ddiv(pick(live, ms, 1.0), kStepSize);
         if (c1) { s.p[kOpp1].tx = v1x; s.p[kOpp1].ty = v1y; s.p[kOpp1].sp = sp; }
         if (c2) { s.p[kOpp2].tx = v2x; s.p[kOpp2].ty = v2y; s.p[kOpp2].sp = sp; }
     }

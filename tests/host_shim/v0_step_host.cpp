@@ -10,6 +10,7 @@
 #define __forceinline__ inline
 #define __noinline__
 #define FUTBOL_ENV_THREADS 1
+#define FUTBOL_HOST_SHIM 1
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }

@@ -1,0 +1,23 @@
+"""Headline counters of an ncu report (one line per metric): python tools/ncu_summary.py rep.ncu-rep"""
+import csv, io, subprocess, sys
+out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, units = rows[0], rows[1]
+keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__sass_average_branch_targets_threads_uniform.pct",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum"]
+for r in rows[2:]:
+    d = dict(zip(hdr, r))
+    for k in keys:
+        if k in d:
+            print("%-70s %s %s" % (k, d[k], units[hdr.index(k)]))
+    st = {k: float(v) for k, v in d.items() if k.startswith("smsp__pcsamp_warps_issue_stalled") and "not_issued" not in k}
+    tot = sum(st.values())
+    for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:10]:
+        print("  stall %-40s %5.1f%%" % (k[len("smsp__pcsamp_warps_issue_stalled_"):], 100 * v / tot))
