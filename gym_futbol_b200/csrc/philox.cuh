@@ -95,12 +95,21 @@ struct StepRng {
         return philox_step_word(seed(), env_id, stream, t, idx);
     }
 
-    __device__ __forceinline__ uint32_t take() { return word_at(j++); }
+    // CHECKED = false: the caller guarantees that the cursor is below kPreDraws at this site (v0: every
+    // site before ai_2's turn, see the draw budget in v0_step.cuh), so the draw is a bare LDS.
+    template <bool CHECKED>
+    __device__ __forceinline__ uint32_t take()
+    {
+        const uint32_t w = CHECKED ? word_at(j) : col[j * kEnvThreads];
+        j += 1;
+        return w;
+    }
     // the word at the cursor; consumed only if `c` (the value is ignored by the caller otherwise)
+    template <bool CHECKED>
     __device__ __forceinline__ uint32_t take_if(bool c)
     {
         uint32_t w = 0;
-        if (j < (uint32_t)kPreDraws) w = col[j * kEnvThreads];
+        if (!CHECKED || j < (uint32_t)kPreDraws) w = col[j * kEnvThreads];
         else if (c) w = philox_step_word(seed(), env_id, stream, t, j);
         j += c ? 1u : 0u;
         return w;

@@ -115,7 +115,8 @@ __device__ __forceinline__ double fm_log(double x)
     return dsub(dmul(dk, ln2_hi), dsub(dsub(hfsq, dadd(dmul(s, dadd(hfsq, R)), dmul(dk, ln2_lo))), f));
 }
 
-__device__ __forceinline__ void fm_sincos(double x, double &sn, double &cs)
+// out of line: only the kick uses it (twice), a few lanes per warp
+static __device__ __noinline__ void fm_sincos(double x, double &sn, double &cs)
 {
     const double invpio2 = 6.36619772367581382433e-01, pio2_1 = 1.57079632673412561417e+00,
         pio2_1t = 6.07710050650619224932e-11;
@@ -170,6 +171,13 @@ __device__ __forceinline__ void reset_env(V0State &s)
 // whole ball row (:465-466), which cancels the pending kick.
 struct PendingShot { int shooter; int target_y; uint32_t pick_idx; };
 
+// Draw budget of a step (sequential draws; the kick's normal() slots are addressed separately).  In turn
+// order: [random_opp: 1 | hard-coded: <= 1, only the opponent holding the ball can draw in get_action_type],
+// then per player 1 (target_y) + 1 if it draws (+1 more for the single possible shooter).  The cursor
+// before a site is therefore at most: opp_1 turn 1, 2, 3; opp_2 turn 4, 5; ai_1 turn 6, 7 (+ pick 8);
+// ai_2 turn 8, 9 (+ pick 10) -- a step consumes at most 10 draws, and only ai_2's sites (and a kick's pick)
+// can reach past the kPreDraws = 8 words parked in shared memory, so only those carry the range check.
+
 // _set_vector_observation, :300-530, for one player: straight-line, predicated.
 template <int AGENT>
 __device__ __forceinline__ void player_turn(V0State &s, V0Rng &rng, const V0Params &P, bool has_ball, int action,
@@ -180,13 +188,14 @@ __device__ __forceinline__ void player_turn(V0State &s, V0Rng &rng, const V0Para
     Row &ao = s.p[AGENT];
     const Row &mate = s.p[AGENT ^ 1];
 
-    const int target_y = 32 + (int)__umulhi(rng.take(), 5u);             // randint(32, 36), :306 -- always drawn first
+    constexpr bool kChecked = AGENT == kAI2;                             // see "Draw budget" above
+    const int target_y = 32 + (int)__umulhi(rng.take<kChecked>(), 5u);   // randint(32, 36), :306 -- always drawn first
     const bool is_run = action == kRun, is_int = action == kIntercept;
     const bool hb_run = has_ball && is_run, hb_int = has_ball && is_int;
     const bool hb_shoot = has_ball && action == kShoot, hb_assist = has_ball && action == kAssist;
     const bool nb_int = !has_ball && is_int;
     // one more draw in: has-ball run (:353), shoot (:367), assist (:416); no-ball intercept (:459, even when far)
-    const uint32_t w = rng.take_if(has_ball != is_int);
+    const uint32_t w = rng.take_if<kChecked>(has_ball != is_int);
     const double u = (double)(w >> 8) * (1.0 / 16777216.0);
 
     const double bx = dsub(s.b.x, ao.x), by = dsub(s.b.y, ao.y);         // :432
@@ -288,7 +297,7 @@ __device__ __forceinline__ int easy_action(const V0State &s, V0Rng &rng, bool ha
     const bool in_range = ao.x <= 20.0;                                  // :77-79, shoot_x = 0 + 20
     const bool open_mate = mo.x < ao.x || mo.y < dsub(ao.y, 7.0) || mo.y > dadd(ao.y, 7.0);   // :81-83
     // the draw happens only when the geometric clause holds (short-circuit `and`, :81-85)
-    const uint32_t w = rng.take_if(has_ball && !in_range && open_mate);
+    const uint32_t w = rng.take_if<false>(has_ball && !in_range && open_mate);
     const bool lucky = (double)(w >> 8) * (1.0 / 16777216.0) > 0.8;
     const bool far_mate = sqsum(dsub(mo.x, ao.x), dsub(mo.y, ao.y)) > kSqGt12;                // distance > 12
     const bool ball_close = sqsum(dsub(s.b.x, ao.x), dsub(s.b.y, ao.y)) <= kSqLe1;           // distance <= 1.0, :90
@@ -298,17 +307,21 @@ __device__ __forceinline__ int easy_action(const V0State &s, V0Rng &rng, bool ha
 }
 
 // _step_by_observation, :560-571 (DECELERATION = 0: the ball's speed update is `sp -= 0.0`).
-// A zero component (0 / mag = that same signed zero) is kept off the divider's slow path.
+// Straight-line: a stopped row (|t| == 0, :563) and a zero component (0 / mag = that same signed zero) are
+// fed benign operands so that every lane stays on the fast path of sqrt/div, and the five rows of a step
+// interleave in the instruction stream instead of being fenced by branches.
 __device__ __forceinline__ void advance(Row &o)
 {
     const double s2 = sqsum(o.tx, o.ty);                                 // :562; sqrt(s2) == 0 <=> s2 == 0
-    if (s2 != 0.0) {
-        const double mag = __dsqrt_rn(s2);
-        const double nx = dmul(o.tx, kStepSize), ny = dmul(o.ty, kStepSize);
-        const double qx = ddiv(pick(nx == 0.0, mag, nx), mag), qy = ddiv(pick(ny == 0.0, mag, ny), mag);
-        o.x = dadd(o.x, dmul(o.sp, nx == 0.0 ? nx : qx));                // :567
-        o.y = dadd(o.y, dmul(o.sp, ny == 0.0 ? ny : qy));                // :568
-    }
+    const bool moving = s2 != 0.0;
+    const double mag = __dsqrt_rn(pick(moving, s2, 1.0));
+    const double nx = dmul(o.tx, kStepSize), ny = dmul(o.ty, kStepSize);
+    const bool zx = nx == 0.0, zy = ny == 0.0;
+    const double qx = ddiv(pick(zx, mag, nx), mag), qy = ddiv(pick(zy, mag, ny), mag);
+    const double x1 = dadd(o.x, dmul(o.sp, zx ? nx : qx));               // :567
+    const double y1 = dadd(o.y, dmul(o.sp, zy ? ny : qy));               // :568
+    o.x = moving ? x1 : o.x;
+    o.y = moving ? y1 : o.y;
 }
 
 // _opp_team_set_vector_observation, :864-982
@@ -381,7 +394,7 @@ __device__ __forceinline__ StepResult v0_step(V0State &s, const V0Params &P, uin
     const bool own_forward_pass = s.b.tx > s.b.ty && s.b.tx > 0.0 && s.b.x > s.p[kAI1].x && s.b.x > s.p[kAI2].x && pre_none;  // :831 (Q6)
 
     if (RANDOM_OPP) {                                                    // :639-645
-        const int r = (int)__umulhi(rng.take(), 16u);                    // randint(0, 15)
+        const int r = (int)__umulhi(rng.take<false>(), 16u);             // randint(0, 15)
         player_turn<kOpp1>(s, rng, P, s.owner == kOpp1, r >> 2, false, 0, 0, shot);
         player_turn<kOpp2>(s, rng, P, s.owner == kOpp2, r & 3, false, 0, 0, shot);
     } else {
