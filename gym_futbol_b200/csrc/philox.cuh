@@ -13,12 +13,14 @@ constexpr uint32_t kStreamV1Opp = 2;      // v1 opponent actions
 constexpr uint32_t kStreamV1Dynamics = 3; // v1 environment draws
 constexpr uint32_t kNormalBlock0 = 0x8000u; // first Philox block of a step's normal() slots
 
-// Threads per block of every kernel that steps environments = stride of the shared-memory draw buffer.
-#ifndef FUTBOL_ENV_THREADS
-#define FUTBOL_ENV_THREADS 128
+// Per-environment working storage lives in shared memory as one column per lane of the owning warp:
+// element k of lane l at base[k * kLanes + l], so a warp-wide access is conflict-free whatever k is.
+#ifndef FUTBOL_LANES
+#define FUTBOL_LANES 32
 #endif
-constexpr int kEnvThreads = FUTBOL_ENV_THREADS;
-constexpr int kPreDraws = 8;              // draws generated up front per step (2 Philox blocks)
+constexpr int kLanes = FUTBOL_LANES;
+constexpr int kSeqBlocks = 3;             // sequential draws generated per step: 12 words (a step uses <= 10)
+constexpr int kDrawWords = 4 * kSeqBlocks;
 
 struct Philox4 { uint32_t x, y, z, w; };
 
@@ -55,68 +57,19 @@ __device__ __forceinline__ Philox4 philox_step_block(const PhiloxKey &K, uint32_
     return philox4x32_10((uint32_t)t, ((uint32_t)(t >> 32) & 0xFFFFu) | (block << 16), env_id, stream, K);
 }
 
-// draws past the pre-generated ones: out of line, a step needs at most 10 and almost always <= 8
-static __device__ __noinline__ uint32_t philox_step_word(uint64_t seed, uint32_t env_id, uint32_t stream, uint64_t t,
-                                                         uint32_t idx)
+// The sequential draws of one step.  The reference consumes a state-dependent number of draws in a
+// state-dependent order, so the position of the next draw is data.  All kDrawWords words a step can need
+// are generated up front (one rolled loop: a single copy of the ten rounds in the instruction stream) and
+// parked in this lane's shared-memory column; a draw is then one LDS at a data-dependent row.
+__device__ __forceinline__ void philox_fill_step(uint32_t *col, const PhiloxKey &K, uint32_t env_id, uint32_t stream, uint64_t t)
 {
-    const PhiloxKey K = philox_expand_key(seed);
-    const Philox4 p = philox_step_block(K, env_id, stream, t, idx >> 2);
-    const uint32_t lo = (idx & 1u) ? p.y : p.x, hi = (idx & 1u) ? p.w : p.z;
-    return (idx & 2u) ? hi : lo;
+#pragma unroll 1
+    for (int b = 0; b < kSeqBlocks; ++b) {
+        const Philox4 p = philox_step_block(K, env_id, stream, t, (uint32_t)b);
+        uint32_t *dst = col + 4 * b * kLanes;
+        dst[0] = p.x; dst[kLanes] = p.y; dst[2 * kLanes] = p.z; dst[3 * kLanes] = p.w;
+    }
 }
-
-// The sequential per-step draw stream.  The reference consumes a state-dependent number of draws in
-// a state-dependent order, so the position `j` of the next draw is data; a register array indexed by
-// data would cost a select tree per draw (or live in local memory).  The first kPreDraws words of the
-// step are therefore parked in shared memory, one column per thread (word k of thread `tid` at
-// buf[k * kEnvThreads + tid]: every lane hits its own bank whatever its j), and a draw is one LDS.
-struct StepRng {
-    const uint32_t *col;
-    const PhiloxKey *key;
-    uint64_t t;
-    uint32_t env_id, stream, j;
-
-    __device__ __forceinline__ uint64_t seed() const { return (uint64_t)key->k0[0] | ((uint64_t)key->k1[0] << 32); }
-
-    __device__ __forceinline__ void begin(uint32_t *col_, const PhiloxKey &key_, uint32_t env_id_, uint32_t stream_, uint64_t t_)
-    {
-        col = col_; key = &key_; env_id = env_id_; stream = stream_; t = t_; j = 0;
-#pragma unroll
-        for (int b = 0; b < kPreDraws / 4; ++b) {
-            const Philox4 p = philox_step_block(*key, env_id, stream, t, b);
-            col_[(4 * b + 0) * kEnvThreads] = p.x; col_[(4 * b + 1) * kEnvThreads] = p.y;
-            col_[(4 * b + 2) * kEnvThreads] = p.z; col_[(4 * b + 3) * kEnvThreads] = p.w;
-        }
-    }
-
-    __device__ __forceinline__ uint32_t word_at(uint32_t idx) const
-    {
-        if (idx < (uint32_t)kPreDraws) return col[idx * kEnvThreads];
-        return philox_step_word(seed(), env_id, stream, t, idx);
-    }
-
-    // CHECKED = false: the caller guarantees that the cursor is below kPreDraws at this site (v0: every
-    // site before ai_2's turn, see the draw budget in v0_step.cuh), so the draw is a bare LDS.
-    template <bool CHECKED>
-    __device__ __forceinline__ uint32_t take()
-    {
-        const uint32_t w = CHECKED ? word_at(j) : col[j * kEnvThreads];
-        j += 1;
-        return w;
-    }
-    // the word at the cursor; consumed only if `c` (the value is ignored by the caller otherwise)
-    template <bool CHECKED>
-    __device__ __forceinline__ uint32_t take_if(bool c)
-    {
-        uint32_t w = 0;
-        if (!CHECKED || j < (uint32_t)kPreDraws) w = col[j * kEnvThreads];
-        else if (c) w = philox_step_word(seed(), env_id, stream, t, j);
-        j += c ? 1u : 0u;
-        return w;
-    }
-};
-
-typedef StepRng V0Rng;
 
 __device__ __forceinline__ int philox_action(const PhiloxKey &K, uint32_t env_id, uint64_t t, uint32_t n_actions)
 {

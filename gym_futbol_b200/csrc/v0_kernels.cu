@@ -6,7 +6,8 @@
 //   uint64  t_total[np]
 //   int32   ep_step[np], ai_score[np], opp_score[np]
 //   uint8   owner[np], last_owner[np], flags[np]
-// = 223 bytes per env.
+// = 223 bytes per env.  Inside a kernel the 25 doubles of an environment sit in shared memory (one column
+// per lane, v0_step.cuh) and the scalars in registers; HBM is touched at the two ends of a launch only.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/futbol_b200.h"
@@ -40,31 +41,24 @@ __host__ __device__ inline StateView make_view(void *base, int n)
     return v;
 }
 
-__device__ __forceinline__ void load_state(const StateView &v, int i, V0State &s)
+constexpr int kEnvThreads = 128;                                  // threads per block of every env kernel
+constexpr int kEnvSmemBytes = (kEnvThreads / 32) * kWarpSmemBytes;   // dynamic shared memory per block
+
+__device__ __forceinline__ void load_state(const StateView &v, int i, Lane L, V0Regs &s)
 {
     const double *f = v.f + i;
-    const size_t np = v.np;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        s.p[r].x = f[(r * 5 + 0) * np]; s.p[r].y = f[(r * 5 + 1) * np]; s.p[r].tx = f[(r * 5 + 2) * np];
-        s.p[r].ty = f[(r * 5 + 3) * np]; s.p[r].sp = f[(r * 5 + 4) * np];
-    }
-    s.b.x = f[20 * np]; s.b.y = f[21 * np]; s.b.tx = f[22 * np]; s.b.ty = f[23 * np]; s.b.sp = f[24 * np];
+    for (int k = 0; k < 25; ++k) L.f(k * kLanes) = f[(size_t)k * v.np];
     s.t_total = v.t_total[i];
     s.ep_step = v.ep_step[i]; s.ai_score = v.ai_score[i]; s.opp_score = v.opp_score[i];
     s.owner = v.owner[i]; s.last_owner = v.last_owner[i];
 }
 
-__device__ __forceinline__ void store_state(const StateView &v, int i, const V0State &s, int flags)
+__device__ __forceinline__ void store_state(const StateView &v, int i, Lane L, const V0Regs &s, int flags)
 {
     double *f = v.f + i;
-    const size_t np = v.np;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        f[(r * 5 + 0) * np] = s.p[r].x; f[(r * 5 + 1) * np] = s.p[r].y; f[(r * 5 + 2) * np] = s.p[r].tx;
-        f[(r * 5 + 3) * np] = s.p[r].ty; f[(r * 5 + 4) * np] = s.p[r].sp;
-    }
-    f[20 * np] = s.b.x; f[21 * np] = s.b.y; f[22 * np] = s.b.tx; f[23 * np] = s.b.ty; f[24 * np] = s.b.sp;
+    for (int k = 0; k < 25; ++k) f[(size_t)k * v.np] = L.f(k * kLanes);
     v.t_total[i] = s.t_total;
     v.ep_step[i] = s.ep_step; v.ai_score[i] = s.ai_score; v.opp_score[i] = s.opp_score;
     v.owner[i] = (uint8_t)s.owner; v.last_owner[i] = (uint8_t)s.last_owner; v.flags[i] = (uint8_t)flags;
@@ -73,45 +67,53 @@ __device__ __forceinline__ void store_state(const StateView &v, int i, const V0S
 // ---- observation output ------------------------------------------------------------------------
 // A thread's observation is 30 consecutive values, so lane-strided stores would touch 30 cache lines
 // per instruction.  fp32 rows are therefore staged through shared memory per warp and written out as
-// consecutive 128-bit stores (a warp's 32 rows are one contiguous 3840-byte span of [n, 30]).
-constexpr int kObsDim = 30;
-
-__device__ __forceinline__ void warp_store_obs_f32(float *smem_warp, const V0State &s, float *gdst_warp_row0,
+// consecutive 128-bit stores (a warp's 32 rows are one contiguous 3840-byte span of [n, 30]).  The
+// staging area reuses the space of the step's draw words (dead by now), hence the leading __syncwarp.
+__device__ __forceinline__ void warp_store_obs_f32(Lane L, const V0Regs &s, float *stage, float *gdst_warp_row0,
                                                    int lane, int rows_in_warp, bool vec_ok)
 {
-    for_each_obs(s, [&](int k, double v) { smem_warp[lane * kObsDim + k] = (float)v; });
+    __syncwarp();
+    float *mine = stage + lane * kObsDim;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) mine[k] = (float)L.f(k * kLanes);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) mine[25 + k] = (float)obs_owner_elem(s, k);
     __syncwarp();
     const int total = rows_in_warp * kObsDim;
     if (vec_ok) {
         const int nvec = total >> 2;
-        const float4 *src = reinterpret_cast<const float4 *>(smem_warp);
+        const float4 *src = reinterpret_cast<const float4 *>(stage);
         float4 *dst = reinterpret_cast<float4 *>(gdst_warp_row0);
         for (int q = lane; q < nvec; q += 32) __stcs(dst + q, src[q]);
-        for (int q = (nvec << 2) + lane; q < total; q += 32) __stcs(gdst_warp_row0 + q, smem_warp[q]);
+        for (int q = (nvec << 2) + lane; q < total; q += 32) __stcs(gdst_warp_row0 + q, stage[q]);
     } else {
-        for (int q = lane; q < total; q += 32) __stcs(gdst_warp_row0 + q, smem_warp[q]);
+        for (int q = lane; q < total; q += 32) __stcs(gdst_warp_row0 + q, stage[q]);
     }
     __syncwarp();
 }
 
 template <typename T>
-__device__ __forceinline__ void thread_store_obs(T *dst_row, const V0State &s)
+__device__ __forceinline__ void thread_store_obs(T *dst_row, Lane L, const V0Regs &s)
 {
-    for_each_obs(s, [&](int k, double v) { dst_row[k] = (T)v; });
+#pragma unroll
+    for (int k = 0; k < 25; ++k) dst_row[k] = (T)L.f(k * kLanes);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) dst_row[25 + k] = (T)obs_owner_elem(s, k);
 }
 
 // ---- reset ---------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(128) v0_reset_kernel(V0Params P, StateView v, const uint8_t *mask, T *obs, int init)
+__global__ void __launch_bounds__(kEnvThreads) v0_reset_kernel(V0Params P, StateView v, const uint8_t *mask, T *obs, int init)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_envs) return;
     if (mask != nullptr && mask[i] == 0) return;
-    V0State s;
+    const Lane L = make_lane(threadIdx.x >> 5, threadIdx.x & 31);
+    V0Regs s;
     s.t_total = init ? 0 : v.t_total[i];
-    reset_env(s);
-    store_state(v, i, s, 0);
-    if (obs != nullptr) thread_store_obs(obs + (size_t)i * kObsDim, s);
+    reset_env(L, s);
+    store_state(v, i, L, s, 0);
+    if (obs != nullptr) thread_store_obs(obs + (size_t)i * kObsDim, L, s);
 }
 
 // ---- per-step API ----------------------------------------------------------------------------------
@@ -119,35 +121,32 @@ template <typename T, bool RANDOM_OPP>
 __global__ void __launch_bounds__(kEnvThreads) v0_step_kernel(V0Params P, StateView v, const uint8_t *actions, T *obs,
                                                               T *reward, uint8_t *done, T *final_obs)
 {
-    __shared__ uint32_t draws[kPreDraws * kEnvThreads];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_envs) return;
-    V0State s;
-    load_state(v, i, s);
-    const StepResult r = v0_step<RANDOM_OPP>(s, P, P.env_id_offset + (uint32_t)i, actions[i] & 15, draws + threadIdx.x);
+    const Lane L = make_lane(threadIdx.x >> 5, threadIdx.x & 31);
+    V0Regs s;
+    load_state(v, i, L, s);
+    const StepResult r = v0_step<RANDOM_OPP>(L, s, P, P.env_id_offset + (uint32_t)i, actions[i] & 15);
     if (r.done && P.auto_reset) {
-        if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * kObsDim, s);
-        reset_env(s);
+        if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * kObsDim, L, s);
+        reset_env(L, s);
     }
-    store_state(v, i, s, r.flags);
-    if (obs != nullptr) thread_store_obs(obs + (size_t)i * kObsDim, s);
+    store_state(v, i, L, s, r.flags);
+    if (obs != nullptr) thread_store_obs(obs + (size_t)i * kObsDim, L, s);
     if (reward != nullptr) reward[i] = (T)r.reward;
     if (done != nullptr) done[i] = (uint8_t)r.done;
 }
 
 // ---- fused K-step rollout ----------------------------------------------------------------------------
-constexpr int kRolloutThreads = kEnvThreads;
 #ifndef FUTBOL_MIN_BLOCKS
-#define FUTBOL_MIN_BLOCKS 4     // resident blocks per SM the register allocation is sized for
+#define FUTBOL_MIN_BLOCKS 5     // resident blocks per SM the register allocation is sized for (shared memory allows 5)
 #endif
 
 template <bool RANDOM_OPP>
-__global__ void __launch_bounds__(kRolloutThreads, FUTBOL_MIN_BLOCKS)
+__global__ void __launch_bounds__(kEnvThreads, FUTBOL_MIN_BLOCKS)
 v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ actions, float *__restrict__ obs,
                   float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
 {
-    __shared__ __align__(16) float stage[kRolloutThreads / 32][32 * kObsDim];
-    __shared__ uint32_t draws[kPreDraws * kEnvThreads];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warp_env0 = i - lane;
@@ -158,37 +157,40 @@ v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ ac
     // 128-bit stores need every step's row block 16-byte aligned: n*30*4 % 16 == 0  <=>  n even
     const bool vec_ok = ((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
     const uint32_t env_id = P.env_id_offset + (uint32_t)i;
+    const Lane L = make_lane(warp, lane);
+    float *stage = reinterpret_cast<float *>(futbol_smem + warp * kWarpSmemBytes + kWarpStateBytes);
 
-    V0State s;
-    if (live) load_state(v, i, s);
-    else { s.t_total = 0; reset_env(s); }
+    V0Regs s;
+    if (live) load_state(v, i, L, s);
+    else { s.t_total = 0; reset_env(L, s); }      // padding lanes of the last warp step a private dummy env
 
     double reward_sum = 0.0;
     uint32_t episodes = 0, goals_ai = 0, goals_opp = 0, fixes = 0;
     int last_flags = 0;
 
+#pragma unroll 1
     for (int k = 0; k < K; ++k) {
         const size_t slot = (size_t)k * n + (size_t)i;
         int a;
         if (actions != nullptr) a = live ? (__ldg(actions + slot) & 15) : 0;
         else a = philox_action(P.key, env_id, s.t_total, 16);
         const int ai_before = s.ai_score;
-        const StepResult r = v0_step<RANDOM_OPP>(s, P, env_id, a, draws + threadIdx.x);
+        const StepResult r = v0_step<RANDOM_OPP>(L, s, P, env_id, a);
         last_flags = r.flags;
         reward_sum += r.reward;
         goals_ai += (r.flags & kFlagGoal) && s.ai_score != ai_before;
         goals_opp += (r.flags & kFlagGoal) && s.ai_score == ai_before;
         fixes += (r.flags & kFlagFix) != 0;
         episodes += r.done;
-        if (r.done && P.auto_reset) reset_env(s);
+        if (r.done && P.auto_reset) reset_env(L, s);
         if (obs != nullptr)
-            warp_store_obs_f32(stage[warp], s, obs + ((size_t)k * n + (size_t)warp_env0) * kObsDim, lane, rows_in_warp, vec_ok);
+            warp_store_obs_f32(L, s, stage, obs + ((size_t)k * n + (size_t)warp_env0) * kObsDim, lane, rows_in_warp, vec_ok);
         if (live) {
             if (reward != nullptr) __stcs(reward + slot, (float)r.reward);
             if (done != nullptr) done[slot] = (uint8_t)r.done;
         }
     }
-    if (live) store_state(v, i, s, last_flags);
+    if (live) store_state(v, i, L, s, last_flags);
 
     if (stats != nullptr) {
         if (!live) { reward_sum = 0.0; episodes = goals_ai = goals_opp = fixes = 0; }
@@ -240,8 +242,9 @@ cudaError_t v0_launch_reset(const V0Params &P, void *state, const uint8_t *mask,
                             cudaStream_t st)
 {
     const StateView v = make_view(state, P.n_envs);
-    if (obs_f64) v0_reset_kernel<double><<<blocks_for(P.n_envs, 128), 128, 0, st>>>(P, v, mask, (double *)obs, init);
-    else v0_reset_kernel<float><<<blocks_for(P.n_envs, 128), 128, 0, st>>>(P, v, mask, (float *)obs, init);
+    const int blocks = blocks_for(P.n_envs, kEnvThreads);
+    if (obs_f64) v0_reset_kernel<double><<<blocks, kEnvThreads, kEnvSmemBytes, st>>>(P, v, mask, (double *)obs, init);
+    else v0_reset_kernel<float><<<blocks, kEnvThreads, kEnvSmemBytes, st>>>(P, v, mask, (float *)obs, init);
     return cudaGetLastError();
 }
 
@@ -249,8 +252,8 @@ template <typename T, bool RANDOM_OPP>
 static void launch_step(const V0Params &P, const StateView &v, const uint8_t *actions, void *obs, void *reward,
                         uint8_t *done, void *final_obs, cudaStream_t st)
 {
-    v0_step_kernel<T, RANDOM_OPP><<<blocks_for(P.n_envs, kEnvThreads), kEnvThreads, 0, st>>>(P, v, actions, (T *)obs, (T *)reward,
-                                                                                         done, (T *)final_obs);
+    v0_step_kernel<T, RANDOM_OPP><<<blocks_for(P.n_envs, kEnvThreads), kEnvThreads, kEnvSmemBytes, st>>>(
+        P, v, actions, (T *)obs, (T *)reward, done, (T *)final_obs);
 }
 
 cudaError_t v0_launch_step(const V0Params &P, void *state, const uint8_t *actions, void *obs, void *reward,
@@ -271,9 +274,9 @@ cudaError_t v0_launch_rollout(const V0Params &P, void *state, int K, const uint8
                               uint8_t *done, FutbolStats *stats, cudaStream_t st)
 {
     const StateView v = make_view(state, P.n_envs);
-    const int blocks = blocks_for(P.n_envs, kRolloutThreads);
-    if (P.random_opp) v0_rollout_kernel<true><<<blocks, kRolloutThreads, 0, st>>>(P, v, K, actions, obs, reward, done, stats);
-    else v0_rollout_kernel<false><<<blocks, kRolloutThreads, 0, st>>>(P, v, K, actions, obs, reward, done, stats);
+    const int blocks = blocks_for(P.n_envs, kEnvThreads);
+    if (P.random_opp) v0_rollout_kernel<true><<<blocks, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, actions, obs, reward, done, stats);
+    else v0_rollout_kernel<false><<<blocks, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, actions, obs, reward, done, stats);
     return cudaGetLastError();
 }
 

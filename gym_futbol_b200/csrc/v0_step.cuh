@@ -1,6 +1,6 @@
-// Device-side v0 environment step: one thread owns one environment, all 25 state doubles live in
-// registers.  Replaces gym_futbol/envs/futbol_env.py FutbolEnv.step (:628-717) and everything it
-// calls, including Easy_Agent.get_action_type (gym_futbol/envs/easy_agent.py:53-98).
+// Device-side v0 environment step: one thread owns one environment.  Replaces
+// gym_futbol/envs/futbol_env.py FutbolEnv.step (:628-717) and everything it calls, including
+// Easy_Agent.get_action_type (gym_futbol/envs/easy_agent.py:53-98).
 //
 // Arithmetic contract ("kernel arithmetic"): fp64, the reference's operation order, no FMA
 // contraction (every product and sum goes through __dmul_rn/__dadd_rn/..., which the compiler never
@@ -8,16 +8,20 @@
 // specified fm_log/fm_sincos below (fdlibm-style polynomials, individually rounded IEEE operations in a
 // fixed order), so that a CPU restatement of the same specification agrees BIT for bit.
 //
-// Shape of the code ("branch-lean").  The reference picks one of eight branches per player
-// (has-ball x action); the 32 environments of a warp pick 32 different ones, so a branchy transcription
-// executes the union of all branches at ~13 active lanes and, inlined four times, overflows the 32 KB
-// instruction cache (ncu: 76 % of stall samples "no instruction").  Here every player turn is ONE
-// straight-line block: the case is classified into predicates, the single vector magnitude any case
-// needs is computed once, results are committed with selects.  What stays behind a branch is rare:
-// the kick (screw_vec: log, sin, cos) -- deferred to one shared site per step because at most one player
-// can shoot per step -- and draws past the eight pre-generated Philox words.  Threshold tests on a
-// distance (d <= 2, d > 12, ...) are done on the squared distance with the exactly equivalent bound
-// (kSq* below), which removes the square root without changing a single decision.
+// Shape of the code (each choice is an ncu finding, profiles/).
+//  * Branch-lean.  The reference picks one of eight branches per player (has-ball x action); the 32
+//    environments of a warp pick 32 different ones, so a branchy transcription runs the union of all
+//    branches at ~13 active lanes.  Here a player turn is ONE straight-line block: the case is classified
+//    into predicates, the single vector magnitude any case needs is computed once, results are committed
+//    with predicated stores.  What stays behind a branch is rare: the kick (screw_vec: log, sin, cos) --
+//    deferred to one site per step because at most one player can shoot per step.
+//  * Small.  The step is instruction-FETCH bound when unrolled (four inlined player turns + six inlined
+//    kinematics updates = 58 KB of SASS: SM I-cache hit rate 70 %, GPC instruction-cache requests at 95 %
+//    of peak).  The 25 state doubles of an environment therefore live in shared memory, one column per
+//    lane (conflict-free), which makes rows addressable by a RUN-TIME index: one copy of the turn code
+//    looped over the four players, one copy of the kinematics code looped over the five rows.
+//  * Threshold tests on a distance (d <= 2, d > 12, ...) are done on the squared distance with the
+//    exactly equivalent bound (kSq* below): no square root, not a single decision changed.
 #pragma once
 #include <stdint.h>
 #include "philox.cuh"
@@ -51,8 +55,6 @@ constexpr double kLen06 = 63.0;                 // length * 0.6, :931
 constexpr double kDefendX = 78.75, kDefendY = 34.0;   // (length * 0.75, width * 0.5), :933
 constexpr double kRewStolen = -15.0, kRewGained = 18.0, kRewKept = 9.0;   // -50*0.3, 60*0.3, 30*0.3, :832-839
 
-struct Row { double x, y, tx, ty, sp; };
-
 struct V0Params {
     uint64_t seed;
     PhiloxKey key;       // philox_expand_key(seed), set by the host
@@ -65,9 +67,47 @@ struct V0Params {
     double reach_sq_max; // largest s with sqrt_rn(s) < fl(0.1 * player_speed) (:972-976); set by the host
 };
 
-struct V0State {
-    Row p[4];           // ai_1, ai_2, opp_1, opp_2
-    Row b;              // ball
+// ---- per-environment working storage in shared memory ---------------------------------------------------
+// One block of kWarpSmemBytes per warp; element k of lane l of a section at section[k * kLanes + l].
+//   double  st[27][kLanes]   k = 5 * row + field, rows ai_1, ai_2, opp_1, opp_2, ball; fields x, y, tx, ty,
+//                            speed (= observation rows 0-4);  k = 25, 26: the ball's anticipated (x, y)
+//   then, overlapping in time:  uint32 draws[kDrawWords][kLanes]   (during the step)
+//                               float  stage[kLanes * 30]          (observation staging, after the step)
+constexpr int kStateWords = 27;
+constexpr int kNbX = 25, kNbY = 26;
+constexpr int kObsDim = 30;
+constexpr int kWarpStateBytes = kStateWords * kLanes * 8;
+constexpr int kWarpScratchBytes = (kLanes * kObsDim * 4 > kDrawWords * kLanes * 4) ? kLanes * kObsDim * 4 : kDrawWords * kLanes * 4;
+constexpr int kWarpSmemBytes = kWarpStateBytes + kWarpScratchBytes;
+constexpr int kX = 0, kY = kLanes, kTX = 2 * kLanes, kTY = 3 * kLanes, kSP = 4 * kLanes;   // field offsets in a row
+constexpr int kRowStride = 5 * kLanes;
+constexpr int kBallRow = 4;
+
+#ifndef FUTBOL_HOST_SHIM
+extern __shared__ __align__(16) unsigned char futbol_smem[];   // dynamic: (threads / 32) * kWarpSmemBytes
+#else
+static unsigned char futbol_smem[kWarpSmemBytes] __attribute__((aligned(16)));
+#endif
+
+// This lane's columns, as offsets into futbol_smem (an offset, unlike a pointer, keeps its address space
+// through the out-of-line helpers below: every access stays an LDS/STS).
+struct Lane {
+    uint32_t st;   // index (in doubles) of state element 0
+    uint32_t dw;   // index (in uint32) of draw word 0
+    __device__ __forceinline__ double &f(int k) const { return reinterpret_cast<double *>(futbol_smem)[st + k]; }
+    __device__ __forceinline__ uint32_t &draw(uint32_t j) const { return reinterpret_cast<uint32_t *>(futbol_smem)[dw + j * kLanes]; }
+};
+
+__device__ __forceinline__ Lane make_lane(int warp_in_block, int lane)
+{
+    Lane L;
+    L.st = (uint32_t)(warp_in_block * (kWarpSmemBytes / 8) + lane);
+    L.dw = (uint32_t)(warp_in_block * (kWarpSmemBytes / 4) + kWarpStateBytes / 4 + lane);
+    return L;
+}
+
+// the scalar part of an environment's state (registers)
+struct V0Regs {
     uint64_t t_total;
     int ep_step, ai_score, opp_score, owner, last_owner;
 };
@@ -140,22 +180,29 @@ static __device__ __noinline__ void fm_sincos(double x, double &sn, double &cs)
     }
 }
 
-__device__ __forceinline__ void zero_motion(Row &r) { r.tx = 0.0; r.ty = 0.0; r.sp = 0.0; }
+// kickoff formation, futbol_env.py:211-223 (also the goal re-kickoff :684-692).  Out of line: three call
+// sites (goal, reset, padding lanes), 25 stores.
+static __device__ __noinline__ void kickoff_rows(Lane L)
+{
+    const double px[5] = {kFieldLen / 2 - 9, kFieldLen / 2 - 9, kFieldLen / 2 + 9, kFieldLen / 2 + 9, kFieldLen / 2};
+    const double py[5] = {kFieldWid / 2 + 5, kFieldWid / 2 - 5, kFieldWid / 2 + 5, kFieldWid / 2 - 5, kFieldWid / 2};
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        L.f(r * kRowStride + kX) = px[r]; L.f(r * kRowStride + kY) = py[r];
+        L.f(r * kRowStride + kTX) = 0.0; L.f(r * kRowStride + kTY) = 0.0; L.f(r * kRowStride + kSP) = 0.0;
+    }
+}
 
-__device__ __forceinline__ void kickoff(V0State &s)
-{   // futbol_env.py:211-223 (also the goal re-kickoff :684-692)
-    s.b = Row{kFieldLen / 2, kFieldWid / 2, 0, 0, 0};
-    s.p[kAI1] = Row{kFieldLen / 2 - 9, kFieldWid / 2 + 5, 0, 0, 0};
-    s.p[kAI2] = Row{kFieldLen / 2 - 9, kFieldWid / 2 - 5, 0, 0, 0};
-    s.p[kOpp1] = Row{kFieldLen / 2 + 9, kFieldWid / 2 + 5, 0, 0, 0};
-    s.p[kOpp2] = Row{kFieldLen / 2 + 9, kFieldWid / 2 - 5, 0, 0, 0};
+__device__ __forceinline__ void kickoff(Lane L, V0Regs &s)
+{
+    kickoff_rows(L);
     s.owner = kNoOne;
     s.last_owner = kNoOne;
 }
 
-__device__ __forceinline__ void reset_env(V0State &s)
+__device__ __forceinline__ void reset_env(Lane L, V0Regs &s)
 {   // FutbolEnv.reset, :205-245.  t_total (the Philox step index) is deliberately kept.
-    kickoff(s);
+    kickoff(L, s);
     s.ep_step = 0;
     s.ai_score = 0;
     s.opp_score = 0;
@@ -173,42 +220,40 @@ struct PendingShot { int shooter; int target_y; uint32_t pick_idx; };
 
 // Draw budget of a step (sequential draws; the kick's normal() slots are addressed separately).  In turn
 // order: [random_opp: 1 | hard-coded: <= 1, only the opponent holding the ball can draw in get_action_type],
-// then per player 1 (target_y) + 1 if it draws (+1 more for the single possible shooter).  The cursor
-// before a site is therefore at most: opp_1 turn 1, 2, 3; opp_2 turn 4, 5; ai_1 turn 6, 7 (+ pick 8);
-// ai_2 turn 8, 9 (+ pick 10) -- a step consumes at most 10 draws, and only ai_2's sites (and a kick's pick)
-// can reach past the kPreDraws = 8 words parked in shared memory, so only those carry the range check.
+// then per player 1 (target_y) + 1 if it draws (+1 more for the single possible shooter): at most
+// 1 + 4 + 4 + 1 = 10 draws, all inside the kDrawWords = 12 words generated per step, so a draw is a bare LDS.
 
-// _set_vector_observation, :300-530, for one player: straight-line, predicated.
-template <int AGENT>
-__device__ __forceinline__ void player_turn(V0State &s, V0Rng &rng, const V0Params &P, bool has_ball, int action,
-                                            bool set_target, double tgx, double tgy, PendingShot &shot)
+// _set_vector_observation, :300-530, for player `a` (run-time index): straight-line, predicated.
+__device__ __forceinline__ void player_turn(Lane L, uint32_t &j, V0Regs &s, const V0Params &P, int a, bool has_ball,
+                                            int action, bool set_target, double tgx, double tgy, PendingShot &shot)
 {
-    constexpr bool right = AGENT >= kOpp1;
-    constexpr double goal_x = right ? 0.0 : kFieldLen;
-    Row &ao = s.p[AGENT];
-    const Row &mate = s.p[AGENT ^ 1];
+    const int ao = a * kRowStride, mo = (a ^ 1) * kRowStride, bo = kBallRow * kRowStride;
+    const double ax = L.f(ao + kX), ay = L.f(ao + kY), atx = L.f(ao + kTX), aty = L.f(ao + kTY), asp = L.f(ao + kSP);
+    const double mx = L.f(mo + kX), my = L.f(mo + kY);
+    const double ball_x = L.f(bo + kX), ball_y = L.f(bo + kY);
+    const double goal_x = a >= kOpp1 ? 0.0 : kFieldLen;                   // the goal this player attacks
 
-    constexpr bool kChecked = AGENT == kAI2;                             // see "Draw budget" above
-    const int target_y = 32 + (int)__umulhi(rng.take<kChecked>(), 5u);   // randint(32, 36), :306 -- always drawn first
+    const int target_y = 32 + (int)__umulhi(L.draw(j), 5u);              // randint(32, 36), :306 -- always drawn first
+    j += 1;
     const bool is_run = action == kRun, is_int = action == kIntercept;
     const bool hb_run = has_ball && is_run, hb_int = has_ball && is_int;
     const bool hb_shoot = has_ball && action == kShoot, hb_assist = has_ball && action == kAssist;
     const bool nb_int = !has_ball && is_int;
     // one more draw in: has-ball run (:353), shoot (:367), assist (:416); no-ball intercept (:459, even when far)
-    const uint32_t w = rng.take_if<kChecked>(has_ball != is_int);
+    const uint32_t w = L.draw(j);
+    j += (has_ball != is_int) ? 1u : 0u;
     const double u = (double)(w >> 8) * (1.0 / 16777216.0);
 
-    const double bx = dsub(s.b.x, ao.x), by = dsub(s.b.y, ao.y);         // :432
-    const double vx = hb_assist ? dsub(mate.x, s.b.x) : bx;              // :412
-    const double vy = hb_assist ? dsub(mate.y, s.b.y) : by;
+    const double bx = dsub(ball_x, ax), by = dsub(ball_y, ay);           // :432
+    const double vx = hb_assist ? dsub(mx, ball_x) : bx;                 // :412
+    const double vy = hb_assist ? dsub(my, ball_y) : by;
     // The one magnitude a turn needs (no-ball intercept: |ball - player|; has-ball assist: |mate - ball|).
     // sqrt(0) and 0/x leave the fast path of the IEEE sequences (a subroutine call for the lanes that
     // hold the ball, whose ball-player vector is exactly zero), so those lanes are fed a benign operand
     // and the exact result (0) is selected afterwards.
     const double q = sqsum(vx, vy);
     const bool q_zero = q == 0.0;
-    const bool need_mag = nb_int || hb_assist;
-    const double root = __dsqrt_rn(pick(need_mag && !q_zero, q, 1.0));
+    const double root = __dsqrt_rn(pick((nb_int || hb_assist) && !q_zero, q, 1.0));
     const double mag = q_zero ? 0.0 : root;
 
     // has-ball assist, :413-416
@@ -224,54 +269,55 @@ __device__ __forceinline__ void player_turn(V0State &s, V0Rng &rng, const V0Para
     const bool drop = hb_run && u < 0.05;
     const bool carry = hb_run && !drop;
 
-    // the player's own row (Q4: a no-ball intercept keeps the previous vector and speed)
-    if (is_run) {                                                        // :330-352, :483-503 (:503 unreachable, Q12)
-        ao.sp = P.player_speed;
-        ao.tx = set_target ? tgx : (has_ball ? dsub(goal_x, ao.x) : bx);
-        ao.ty = set_target ? tgy : (has_ball ? dsub((double)target_y, ao.y) : by);
-    } else if (!nb_int) {
-        zero_motion(ao);                                                 // :318-321, :383, :423, :509-525
-    }
+    // the player's own row after the turn (Q4: a no-ball intercept keeps the previous vector and speed;
+    // :330-352, :483-503 run (:503 unreachable, Q12); everything else stops :318-321, :383, :423, :509-525)
+    const double run_tx = set_target ? tgx : (has_ball ? dsub(goal_x, ax) : bx);
+    const double run_ty = set_target ? tgy : (has_ball ? dsub((double)target_y, ay) : by);
+    const double rtx = nb_int ? atx : (is_run ? run_tx : 0.0);
+    const double rty = nb_int ? aty : (is_run ? run_ty : 0.0);
+    const double rsp = nb_int ? asp : (is_run ? P.player_speed : 0.0);
+    if (!nb_int) { L.f(ao + kTX) = rtx; L.f(ao + kTY) = rty; L.f(ao + kSP) = rsp; }
     // ball and possession
-    if (carry || take) s.b = ao;                                         // :356, :465-466
-    if (hb_int) zero_motion(s.b);                                        // :321
-    if (hb_assist) { s.b.sp = pass_speed; s.b.tx = vx; s.b.ty = vy; }    // :416-418
-    if (hb_shoot) {                                                      // :367; vector resolved later (PendingShot)
-        s.b.sp = (double)(P.shoot_speed - 16 + (int)__umulhi(w, 17u));
-        shot.shooter = AGENT; shot.target_y = target_y; shot.pick_idx = rng.j;
-        rng.j += 1;                                                      // randint(0, 9) of screw_vec, :107
+    if (carry || take) { L.f(bo + kX) = ax; L.f(bo + kY) = ay; }         // ball row := player row, :356, :465-466
+    if (carry || take || hb_int || hb_assist) {                          // :321 stop, :416-418 pass
+        L.f(bo + kTX) = hb_int ? 0.0 : (hb_assist ? vx : rtx);
+        L.f(bo + kTY) = hb_int ? 0.0 : (hb_assist ? vy : rty);
     }
+    if (carry || take || hb_int || hb_assist || hb_shoot) {              // :367 kick speed; vector resolved later
+        const double kick = (double)(P.shoot_speed - 16 + (int)__umulhi(w, 17u));
+        L.f(bo + kSP) = hb_int ? 0.0 : (hb_assist ? pass_speed : (hb_shoot ? kick : rsp));
+    }
+    if (hb_shoot) { shot.shooter = a; shot.target_y = target_y; shot.pick_idx = j; }
+    j += hb_shoot ? 1u : 0u;                                             // randint(0, 9) of screw_vec, :107
     if (take) shot.shooter = -1;
     if (hb_shoot || hb_assist || take) s.last_owner = s.owner;           // :381, :421, :467
-    s.owner = take ? (int)AGENT : ((drop || hb_shoot || hb_assist) ? (int)kNoOne : s.owner);   // :354, :382, :422, :468
+    s.owner = take ? a : ((drop || hb_shoot || hb_assist) ? (int)kNoOne : s.owner);   // :354, :382, :422, :468
 }
 
 // defence_near (:280-289, with the stale-view behaviour Q1) + screw_vec (:101-116) for the pending kick.
 // By specification (oracle/philox.py) a step's normal() call consumes no sequential draws: slot k lives in
 // Philox block 0x8000 + (k >> 1), words 2(k&1), 2(k&1)+1, so only the block of the picked slot is evaluated.
-__device__ __forceinline__ void resolve_shot(V0State &s, const V0Rng &rng, const V0Params &P, const PendingShot &shot)
+__device__ __forceinline__ void resolve_shot(Lane L, const V0Regs &s, const V0Params &P, bool random_opp, uint32_t env_id,
+                                             const PendingShot &shot)
 {
     const int a = shot.shooter;
     const bool right = a >= kOpp1;
     // the shooter's own position is the frozen kickoff spot, except for hard-coded opponents (views refreshed)
     double px = right ? kFieldLen / 2 + 9 : kFieldLen / 2 - 9;
     double py = (a == kAI1 || a == kOpp1) ? kFieldWid / 2 + 5 : kFieldWid / 2 - 5;
-    if (right && !P.random_opp) {
-        px = a == kOpp1 ? s.p[kOpp1].x : s.p[kOpp2].x;
-        py = a == kOpp1 ? s.p[kOpp1].y : s.p[kOpp2].y;
-    }
-    const double d1x = right ? s.p[kAI1].x : s.p[kOpp1].x, d1y = right ? s.p[kAI1].y : s.p[kOpp1].y;
-    const double d2x = right ? s.p[kAI2].x : s.p[kOpp2].x, d2y = right ? s.p[kAI2].y : s.p[kOpp2].y;
+    if (right && !random_opp) { px = L.f(a * kRowStride + kX); py = L.f(a * kRowStride + kY); }
+    const int d1 = (right ? kAI1 : kOpp1) * kRowStride, d2 = (right ? kAI2 : kOpp2) * kRowStride;
     // bigger_than(d1, d2, 2), :76-82 = how many of the two defenders are within 2.0
-    const int near = (sqsum(dsub(d1x, px), dsub(d1y, py)) <= kSqLe2 ? 1 : 0) +
-                     (sqsum(dsub(d2x, px), dsub(d2y, py)) <= kSqLe2 ? 1 : 0);
+    const int near = (sqsum(dsub(L.f(d1 + kX), px), dsub(L.f(d1 + kY), py)) <= kSqLe2 ? 1 : 0) +
+                     (sqsum(dsub(L.f(d2 + kX), px), dsub(L.f(d2 + kY), py)) <= kSqLe2 ? 1 : 0);
     const double accuracy = dadd(10.0, dmul((double)near, 20.0));        // :364
-    const double vx = dsub(right ? 0.0 : kFieldLen, s.b.x), vy = dsub((double)shot.target_y, s.b.y);   // :373-376
+    const int bo = kBallRow * kRowStride;
+    const double vx = dsub(right ? 0.0 : kFieldLen, L.f(bo + kX)), vy = dsub((double)shot.target_y, L.f(bo + kY));   // :373-376
     const double mag = hyp(vx, vy);
 
-    const uint32_t pick = __umulhi(rng.word_at(shot.pick_idx), 10u);     // randint(0, 9), :107
-    const Philox4 nb = philox_step_block(P.key, rng.env_id, rng.stream, rng.t, kNormalBlock0 + (pick >> 1));
-    const uint32_t w0 = (pick & 1u) ? nb.z : nb.x, w1 = (pick & 1u) ? nb.w : nb.y;
+    const uint32_t pick_slot = __umulhi(L.draw(shot.pick_idx), 10u);     // randint(0, 9), :107
+    const Philox4 nb = philox_step_block(P.key, env_id, kStreamDynamics, s.t_total, kNormalBlock0 + (pick_slot >> 1));
+    const uint32_t w0 = (pick_slot & 1u) ? nb.z : nb.x, w1 = (pick_slot & 1u) ? nb.w : nb.y;
     const double u1 = (double)((w0 >> 8) + 1u) * (1.0 / 16777216.0);
     const double u2 = (double)(w1 >> 8) * (1.0 / 16777216.0);
     double bm_sin, bm_cos;
@@ -284,134 +330,149 @@ __device__ __forceinline__ void resolve_shot(V0State &s, const V0Rng &rng, const
     fm_sincos(swing, ss, sc);                                            // :109-110
     const double tc = dsub(dmul(c, sc), dmul(sn, ss));                   // :113
     const double ts = dadd(dmul(sn, sc), dmul(c, ss));                   // :114
-    s.b.tx = dmul(tc, mag);                                              // :115
-    s.b.ty = dmul(ts, mag);
+    L.f(bo + kTX) = dmul(tc, mag);                                       // :115
+    L.f(bo + kTY) = dmul(ts, mag);
 }
 
-// Easy_Agent.get_action_type for a 'right' opponent, easy_agent.py:53-98
-template <int AGENT>
-__device__ __forceinline__ int easy_action(const V0State &s, V0Rng &rng, bool has_ball, bool team_has_ball)
+// Easy_Agent.get_action_type for 'right' opponent `a`, easy_agent.py:53-98
+__device__ __forceinline__ int easy_action(Lane L, uint32_t &j, int a, bool has_ball, bool team_has_ball)
 {
-    const Row &ao = s.p[AGENT];
-    const Row &mo = s.p[AGENT ^ 1];
-    const bool in_range = ao.x <= 20.0;                                  // :77-79, shoot_x = 0 + 20
-    const bool open_mate = mo.x < ao.x || mo.y < dsub(ao.y, 7.0) || mo.y > dadd(ao.y, 7.0);   // :81-83
+    const int ao = a * kRowStride, mo = (a ^ 1) * kRowStride, bo = kBallRow * kRowStride;
+    const double ax = L.f(ao + kX), ay = L.f(ao + kY), mx = L.f(mo + kX), my = L.f(mo + kY);
+    const bool in_range = ax <= 20.0;                                    // :77-79, shoot_x = 0 + 20
+    const bool open_mate = mx < ax || my < dsub(ay, 7.0) || my > dadd(ay, 7.0);   // :81-83
     // the draw happens only when the geometric clause holds (short-circuit `and`, :81-85)
-    const uint32_t w = rng.take_if<false>(has_ball && !in_range && open_mate);
+    const uint32_t w = L.draw(j);
+    j += (has_ball && !in_range && open_mate) ? 1u : 0u;
     const bool lucky = (double)(w >> 8) * (1.0 / 16777216.0) > 0.8;
-    const bool far_mate = sqsum(dsub(mo.x, ao.x), dsub(mo.y, ao.y)) > kSqGt12;                // distance > 12
-    const bool ball_close = sqsum(dsub(s.b.x, ao.x), dsub(s.b.y, ao.y)) <= kSqLe1;           // distance <= 1.0, :90
+    const bool far_mate = sqsum(dsub(mx, ax), dsub(my, ay)) > kSqGt12;                         // distance > 12
+    const bool ball_close = sqsum(dsub(L.f(bo + kX), ax), dsub(L.f(bo + kY), ay)) <= kSqLe1;  // distance <= 1.0, :90
     const int with_ball = in_range ? (int)kShoot : ((open_mate && lucky && far_mate) ? (int)kAssist : (int)kRun);
-    const int without = (!team_has_ball && ball_close) ? (int)kIntercept : (int)kRun;         // :90-96
+    const int without = (!team_has_ball && ball_close) ? (int)kIntercept : (int)kRun;          // :90-96
     return has_ball ? with_ball : without;
 }
 
-// _step_by_observation, :560-571 (DECELERATION = 0: the ball's speed update is `sp -= 0.0`).
-// Straight-line: a stopped row (|t| == 0, :563) and a zero component (0 / mag = that same signed zero) are
-// fed benign operands so that every lane stays on the fast path of sqrt/div, and the five rows of a step
-// interleave in the instruction stream instead of being fenced by branches.
-__device__ __forceinline__ void advance(Row &o)
+// _step_by_observation, :560-571 (DECELERATION = 0: the ball's speed update is `sp -= 0.0`): reads row
+// `src`, writes the new (x, y) to elements (dx, dy).  Straight-line: a stopped row (|t| == 0, :563) and a
+// zero component (0 / mag = that same signed zero) are fed benign operands so that every lane stays on the
+// fast path of sqrt/div.  Out of line: called from the kinematics loop and from the opponents' anticipation.
+static __device__ __noinline__ void advance_row(Lane L, int src, int dx, int dy)
 {
-    const double s2 = sqsum(o.tx, o.ty);                                 // :562; sqrt(s2) == 0 <=> s2 == 0
+    const double x = L.f(src + kX), y = L.f(src + kY), tx = L.f(src + kTX), ty = L.f(src + kTY), sp = L.f(src + kSP);
+    const double s2 = sqsum(tx, ty);                                     // :562; sqrt(s2) == 0 <=> s2 == 0
     const bool moving = s2 != 0.0;
     const double mag = __dsqrt_rn(pick(moving, s2, 1.0));
-    const double nx = dmul(o.tx, kStepSize), ny = dmul(o.ty, kStepSize);
+    const double nx = dmul(tx, kStepSize), ny = dmul(ty, kStepSize);
     const bool zx = nx == 0.0, zy = ny == 0.0;
     const double qx = ddiv(pick(zx, mag, nx), mag), qy = ddiv(pick(zy, mag, ny), mag);
-    const double x1 = dadd(o.x, dmul(o.sp, zx ? nx : qx));               // :567
-    const double y1 = dadd(o.y, dmul(o.sp, zy ? ny : qy));               // :568
-    o.x = moving ? x1 : o.x;
-    o.y = moving ? y1 : o.y;
+    const double x1 = dadd(x, dmul(sp, zx ? nx : qx));                   // :567
+    const double y1 = dadd(y, dmul(sp, zy ? ny : qy));                   // :568
+    L.f(dx) = moving ? x1 : x;
+    L.f(dy) = moving ? y1 : y;
 }
 
-// _opp_team_set_vector_observation, :864-982
-__device__ __forceinline__ void opp_team(V0State &s, V0Rng &rng, const V0Params &P, PendingShot &shot)
-{
-    const bool has1 = s.owner == kOpp1, has2 = s.owner == kOpp2;         // :866-877 (latched before either acts)
-    const bool team_has = has1 || has2;
-    const int a1 = easy_action<kOpp1>(s, rng, has1, team_has);           // :879
-    const int a2 = easy_action<kOpp2>(s, rng, has2, team_has);           // :880
-    const bool run1 = a1 == kRun, run2 = a2 == kRun;
-    int a1_type = a1, a2_type = a2;                                      // overrides do not touch a1 / a2
-    const Row &o1 = s.p[kOpp1], &o2 = s.p[kOpp2];
-    const bool diag1 = o1.y > kWid02, diag2 = o2.y < kWid08;
-    // carrier runs on the diagonal, its running mate mirrors it, :893-928
-    bool set1 = diag1 && ((has1 && run1) || (has2 && run2 && run1 && o1.x > kLen01));
-    bool set2 = diag2 && ((has2 && run2) || (has1 && run1 && run2 && o2.x > kLen01));
-    double t1x = -1.0, t1y = -1.0, t2x = -1.0, t2y = 1.0;
-    if ((s.owner == kAI1 || s.owner == kAI2) && s.b.x < kLen06) {   // :931-947: the deeper opp defends
-        const double dpx = kDefendX, dpy = kDefendY;
-        if (o1.x > o2.x) { a1_type = kRun; set1 = true; t1x = dsub(dpx, o1.x); t1y = dsub(dpy, o1.y); }
-        else             { a2_type = kRun; set2 = true; t2x = dsub(dpx, o2.x); t2y = dsub(dpy, o2.y); }
-    }
-    player_turn<kOpp1>(s, rng, P, has1, a1_type, set1, t1x, t1y, shot);  // :951-954
-    player_turn<kOpp2>(s, rng, P, has2, a2_type, set2, t2x, t2y, shot);  // :956-959
-    {   // :962-982 anticipate the ball: whoever can reach its next position lands exactly on it
-        Row nb = s.b;
-        advance(nb);
-        const double v1x = dsub(nb.x, s.p[kOpp1].x), v1y = dsub(nb.y, s.p[kOpp1].y);
-        const double v2x = dsub(nb.x, s.p[kOpp2].x), v2y = dsub(nb.y, s.p[kOpp2].y);
-        const double q1 = sqsum(v1x, v1y), q2 = sqsum(v2x, v2y);
-        const bool on = s.owner == kNoOne && run1 && run2;
-        const bool c1 = on && q1 <= P.reach_sq_max;                      // hyp(v1) < 0.1 * player_speed
-        const bool c2 = on && !c1 && q2 <= P.reach_sq_max;
-        const double qs = c1 ? q1 : q2;
-        const bool live = (c1 || c2) && qs != 0.0;                       // others: benign operand, result unused
-        const double ms = __dsqrt_rn(pick(live, qs, 1.0));
-        const double sp = qs == 0.0 ? 0.0 : ddiv(pick(live, ms, 1.0), kStepSize);
-        if (c1) { s.p[kOpp1].tx = v1x; s.p[kOpp1].ty = v1y; s.p[kOpp1].sp = sp; }
-        if (c2) { s.p[kOpp2].tx = v2x; s.p[kOpp2].ty = v2y; s.p[kOpp2].sp = sp; }
-    }
-}
-
-__device__ __forceinline__ bool player_out(const Row &o)
+__device__ __forceinline__ bool out_of_pitch(double x, double y)
 {   // out, :574-577
-    return (o.x < 0.0 || o.x > kFieldLen) || (o.y < 0.0 || o.y > kFieldWid);
+    return (x < 0.0 || x > kFieldLen) || (y < 0.0 || y > kFieldWid);
 }
 
 struct StepResult { double reward; int done; int flags; };
 
-// FutbolEnv.step, :628-717.  `ai_action` in 0..15.  `rng_col`: this thread's column of the shared-memory
-// draw buffer (StepRng).  RANDOM_OPP = the constructor's random_opp (:138), a compile-time variant so that each
-// kernel carries only its own opponent code.
+// FutbolEnv.step, :628-717.  `ai_action` in 0..15.  RANDOM_OPP = the constructor's random_opp (:138), a
+// compile-time variant so that each kernel carries only its own opponent code.
 template <bool RANDOM_OPP>
-__device__ __forceinline__ StepResult v0_step(V0State &s, const V0Params &P, uint32_t env_id, int ai_action,
-                                              uint32_t *rng_col)
+__device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params &P, uint32_t env_id, int ai_action)
 {
-    V0Rng rng;
-    rng.begin(rng_col, P.key, env_id, kStreamDynamics, s.t_total);
+    philox_fill_step(&L.draw(0), P.key, env_id, kStreamDynamics, s.t_total);
+    uint32_t j = 0;
     PendingShot shot;
     shot.shooter = -1; shot.target_y = 0; shot.pick_idx = 0;
+    const int bo = kBallRow * kRowStride;
 
     // pre-step snapshot used by the reward (:630-635).  The owner one-hot row of the observation is all
-    // zeros between reset() and the end of the first step, otherwise 10 * onehot(owner).
+    // zeros between reset() and the end of the first step, otherwise 10 * onehot(owner).  Everything
+    // _get_reward reads from the snapshot is a comparison of pre-step values: evaluate them now.
     const bool fresh = s.ep_step == 0;
     const bool pre_ai1 = !fresh && s.owner == kAI1, pre_ai2 = !fresh && s.owner == kAI2;
     const bool pre_none = !fresh && s.owner == kNoOne;
-    // everything _get_reward reads from the snapshot is a comparison of pre-step values: evaluate them now
-    const bool far1 = sqsum(dsub(s.b.x, s.p[kAI1].x), dsub(s.b.y, s.p[kAI1].y)) > kSqLe2;   // distance > 2, :757, :790
-    const bool far2 = sqsum(dsub(s.b.x, s.p[kAI2].x), dsub(s.b.y, s.p[kAI2].y)) > kSqLe2;   // :758, :799
-    const bool own_forward_pass = s.b.tx > s.b.ty && s.b.tx > 0.0 && s.b.x > s.p[kAI1].x && s.b.x > s.p[kAI2].x && pre_none;  // :831 (Q6)
+    bool far1, far2, own_forward_pass;
+    {
+        const double b_x = L.f(bo + kX), b_y = L.f(bo + kY), b_tx = L.f(bo + kTX), b_ty = L.f(bo + kTY);
+        const double a1x = L.f(kAI1 * kRowStride + kX), a1y = L.f(kAI1 * kRowStride + kY);
+        const double a2x = L.f(kAI2 * kRowStride + kX), a2y = L.f(kAI2 * kRowStride + kY);
+        far1 = sqsum(dsub(b_x, a1x), dsub(b_y, a1y)) > kSqLe2;           // distance > 2, :757, :790
+        far2 = sqsum(dsub(b_x, a2x), dsub(b_y, a2y)) > kSqLe2;           // :758, :799
+        own_forward_pass = b_tx > b_ty && b_tx > 0.0 && b_x > a1x && b_x > a2x && pre_none;   // :831 (Q6)
+    }
 
+    // ---- what the two opponents will do ----
+    int opp_a1, opp_a2;                      // the action each opponent's turn is run with
+    bool has1 = false, has2 = false, set1 = false, set2 = false, run1 = false, run2 = false;
+    double t1x = -1.0, t1y = -1.0, t2x = -1.0, t2y = 1.0;
     if (RANDOM_OPP) {                                                    // :639-645
-        const int r = (int)__umulhi(rng.take<false>(), 16u);             // randint(0, 15)
-        player_turn<kOpp1>(s, rng, P, s.owner == kOpp1, r >> 2, false, 0, 0, shot);
-        player_turn<kOpp2>(s, rng, P, s.owner == kOpp2, r & 3, false, 0, 0, shot);
-    } else {
-        opp_team(s, rng, P, shot);                                       // :649
+        const int r = (int)__umulhi(L.draw(j), 16u);                     // randint(0, 15)
+        j += 1;
+        opp_a1 = r >> 2; opp_a2 = r & 3;
+    } else {                                                             // _opp_team_set_vector_observation, :864-947
+        has1 = s.owner == kOpp1; has2 = s.owner == kOpp2;                // :866-877 (latched before either acts)
+        const bool team_has = has1 || has2;
+        const int a1 = easy_action(L, j, kOpp1, has1, team_has);         // :879
+        const int a2 = easy_action(L, j, kOpp2, has2, team_has);         // :880
+        run1 = a1 == kRun; run2 = a2 == kRun;
+        opp_a1 = a1; opp_a2 = a2;                                        // overrides do not touch a1 / a2
+        const double o1x = L.f(kOpp1 * kRowStride + kX), o1y = L.f(kOpp1 * kRowStride + kY);
+        const double o2x = L.f(kOpp2 * kRowStride + kX), o2y = L.f(kOpp2 * kRowStride + kY);
+        const bool diag1 = o1y > kWid02, diag2 = o2y < kWid08;
+        // carrier runs on the diagonal, its running mate mirrors it, :893-928
+        set1 = diag1 && ((has1 && run1) || (has2 && run2 && run1 && o1x > kLen01));
+        set2 = diag2 && ((has2 && run2) || (has1 && run1 && run2 && o2x > kLen01));
+        if ((s.owner == kAI1 || s.owner == kAI2) && L.f(bo + kX) < kLen06) {   // :931-947: the deeper opp defends
+            if (o1x > o2x) { opp_a1 = kRun; set1 = true; t1x = dsub(kDefendX, o1x); t1y = dsub(kDefendY, o1y); }
+            else           { opp_a2 = kRun; set2 = true; t2x = dsub(kDefendX, o2x); t2y = dsub(kDefendY, o2y); }
+        }
     }
     const int action1 = ai_action >> 2, action2 = ai_action & 3;         // :653
-    player_turn<kAI1>(s, rng, P, s.owner == kAI1, action1, false, 0, 0, shot);   // :655
-    player_turn<kAI2>(s, rng, P, s.owner == kAI2, action2, false, 0, 0, shot);   // :656
-    if (shot.shooter >= 0) resolve_shot(s, rng, P, shot);
 
-#pragma unroll
-    for (int i = 0; i < 4; ++i) advance(s.p[i]);                         // :661
-    advance(s.b);                                                        // :663
+    // ---- the four turns, in the reference's order opp_1, opp_2, ai_1, ai_2 (:639-656): one copy of the code ----
+#pragma unroll 1
+    for (int t = 0; t < 4; ++t) {
+        const int a = (t + 2) & 3;
+        const bool opp = t < 2;
+        const bool latched = !RANDOM_OPP && opp;
+        const bool has_ball = latched ? (t == 0 ? has1 : has2) : s.owner == a;
+        const int action = t == 0 ? opp_a1 : (t == 1 ? opp_a2 : (t == 2 ? action1 : action2));
+        const bool set_target = latched && (t == 0 ? set1 : set2);
+        player_turn(L, j, s, P, a, has_ball, action, set_target, t == 0 ? t1x : t2x, t == 0 ? t1y : t2y, shot);
+        if (!RANDOM_OPP && t == 1) {
+            // :962-982 anticipate the ball: whoever can reach its next position lands exactly on it
+            advance_row(L, bo, kNbX * kLanes, kNbY * kLanes);
+            const double nbx = L.f(kNbX * kLanes), nby = L.f(kNbY * kLanes);
+            const double v1x = dsub(nbx, L.f(kOpp1 * kRowStride + kX)), v1y = dsub(nby, L.f(kOpp1 * kRowStride + kY));
+            const double v2x = dsub(nbx, L.f(kOpp2 * kRowStride + kX)), v2y = dsub(nby, L.f(kOpp2 * kRowStride + kY));
+            const double q1 = sqsum(v1x, v1y), q2 = sqsum(v2x, v2y);
+            const bool on = s.owner == kNoOne && run1 && run2;
+            const bool c1 = on && q1 <= P.reach_sq_max;                  // hyp(v1) < 0.1 * player_speed
+            const bool c2 = on && !c1 && q2 <= P.reach_sq_max;
+            const double qs = c1 ? q1 : q2;
+            const bool live = (c1 || c2) && qs != 0.0;                   // others: benign operand, result unused
+            const double ms = __dsqrt_rn(pick(live, qs, 1.0));
+            const double sp = qs == 0.0 ? 0.0 : ddiv(pick(live, ms, 1.0), kStepSize);
+            if (c1 || c2) {
+                const int ro = (c1 ? kOpp1 : kOpp2) * kRowStride;
+                L.f(ro + kTX) = c1 ? v1x : v2x; L.f(ro + kTY) = c1 ? v1y : v2y; L.f(ro + kSP) = sp;
+            }
+        }
+    }
+    if (shot.shooter >= 0) resolve_shot(L, s, P, RANDOM_OPP, env_id, shot);
+
+    // ---- kinematics, :661-663: one copy of the code over the five rows ----
+#pragma unroll 1
+    for (int r = 0; r < 5; ++r) advance_row(L, r * kRowStride, r * kRowStride + kX, r * kRowStride + kY);
 
     // ---- _get_reward, :752-861 (evaluated before the goal re-kickoff) ----
-    const bool in_mouth = s.b.y > kGoalLower && s.b.y < kGoalUpper;
-    const bool goal_for = s.b.x >= kFieldLen && in_mouth, goal_against = s.b.x <= 0.0 && in_mouth;   // score(), :580-583
+    const double ball_x = L.f(bo + kX), ball_y = L.f(bo + kY);
+    const bool in_mouth = ball_y > kGoalLower && ball_y < kGoalUpper;
+    const bool goal_for = ball_x >= kFieldLen && in_mouth, goal_against = ball_x <= 0.0 && in_mouth;   // score(), :580-583
     double reward;
     {
         const double score = goal_for ? 1000.0 : 0.0, get_scored = goal_against ? -1000.0 : 0.0;
@@ -425,13 +486,15 @@ __device__ __forceinline__ StepResult v0_step(V0State &s, const V0Params &P, uin
             else bad1 = action1 == kIntercept ? -1.0 : 0.0;              // :783-794
             if (!pre_ai2) bad2 = (action2 == kAssist || action2 == kShoot) ? -1.0 : ((far2 && action1 == kIntercept) ? -0.5 : 0.0);  // Q5
             else bad2 = action2 == kIntercept ? -1.0 : 0.0;              // :796-807
-            const double out_r = (player_out(s.p[kAI1]) || player_out(s.p[kAI2])) ? -0.6 : 0.0;   // :823-826
+            const bool ai_out = out_of_pitch(L.f(kAI1 * kRowStride + kX), L.f(kAI1 * kRowStride + kY)) ||
+                                out_of_pitch(L.f(kAI2 * kRowStride + kX), L.f(kAI2 * kRowStride + kY));
+            const double out_r = ai_out ? -0.6 : 0.0;                    // :823-826
             const bool ai_owns = s.owner == kAI1 || s.owner == kAI2;
             double get_ball;
             if (ai_owns && !pre_ai1 && !pre_ai2)                          // :828-836 (Q6)
                 get_ball = own_forward_pass ? kRewStolen : kRewGained;
             else if ((s.owner == kAI1 && pre_ai1) || (s.owner == kAI2 && pre_ai2))
-                get_ball = kRewKept;                                 // :837-839
+                get_ball = kRewKept;                                     // :837-839
             else
                 get_ball = 0.0;
             reward = dadd(dadd(dadd(dadd(dadd(dadd(get_ball, score), get_scored), out_r), dadd(bad1, bad2)), adv_r), running_r);  // :861
@@ -441,22 +504,25 @@ __device__ __forceinline__ StepResult v0_step(V0State &s, const V0Params &P, uin
     StepResult res;
     res.done = 0;
     res.flags = 0;
+    double fx = ball_x, fy = ball_y;                                     // the ball as out_of_field sees it
     if (goal_for || goal_against) {                                      // :670-699
-        if (s.b.x <= 0.0) s.opp_score += 1; else s.ai_score += 1;
+        if (ball_x <= 0.0) s.opp_score += 1; else s.ai_score += 1;
         if (P.one_goal_end) res.done = 1;
-        kickoff(s);
+        kickoff(L, s);
+        fx = kFieldLen / 2; fy = kFieldWid / 2;
         res.flags |= kFlagGoal;
     }
     {   // out_of_field + fix, :621-625, :587-604, :701-707 (Q7, Q8)
-        const bool x_out = s.b.x < 0.0 || s.b.x > kFieldLen, y_out = s.b.y < 0.0 || s.b.y > kFieldWid;
-        const bool y_score = s.b.y > kGoalLower - 2 && s.b.y < kGoalUpper + 2;
+        const bool x_out = fx < 0.0 || fx > kFieldLen, y_out = fy < 0.0 || fy > kFieldWid;
+        const bool y_score = fy > kGoalLower - 2 && fy < kGoalUpper + 2;
         if ((x_out && !y_score) || y_out) {
             const int new_owner = (s.last_owner == kOpp1 || s.last_owner == kOpp2) ? kAI1 : kOpp1;
-            s.b.x = s.b.x < 0.0 ? 0.0 : (s.b.x > kFieldLen ? kFieldLen : s.b.x);   // lock_in, :68-74
-            s.b.y = s.b.y < 0.0 ? 0.0 : (s.b.y > kFieldWid ? kFieldWid : s.b.y);
-            zero_motion(s.b);
+            const double cx = fx < 0.0 ? 0.0 : (fx > kFieldLen ? kFieldLen : fx);   // lock_in, :68-74
+            const double cy = fy < 0.0 ? 0.0 : (fy > kFieldWid ? kFieldWid : fy);
+            const int po = new_owner * kRowStride;                       // the new owner is put on the ball, :601-604
+            L.f(bo + kX) = cx; L.f(bo + kY) = cy; L.f(bo + kTX) = 0.0; L.f(bo + kTY) = 0.0; L.f(bo + kSP) = 0.0;
+            L.f(po + kX) = cx; L.f(po + kY) = cy; L.f(po + kTX) = 0.0; L.f(po + kTY) = 0.0; L.f(po + kSP) = 0.0;
             s.owner = new_owner;
-            if (new_owner == kAI1) s.p[kAI1] = s.b; else s.p[kOpp1] = s.b;
             if (P.one_goal_end) res.done = 1;
             res.flags |= kFlagFix;
         }
@@ -469,22 +535,11 @@ __device__ __forceinline__ StepResult v0_step(V0State &s, const V0Params &P, uin
     return res;
 }
 
-// observation element k (0..29) of the (6,5) array the reference returns (:717)
-__device__ __forceinline__ double obs_elem_owner(const V0State &s, int idx)
-{   // ball_owner_array_update, :720-736; all zeros right after reset (:223)
-    return (s.ep_step != 0 && s.owner == idx) ? 10.0 : 0.0;
-}
-
-template <typename F>
-__device__ __forceinline__ void for_each_obs(const V0State &s, F f)
+// observation element 25 + idx of the (6,5) array the reference returns (:717): ball_owner_array_update,
+// :720-736; all zeros right after reset (:223)
+__device__ __forceinline__ double obs_owner_elem(const V0Regs &s, int idx)
 {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        f(r * 5 + 0, s.p[r].x); f(r * 5 + 1, s.p[r].y); f(r * 5 + 2, s.p[r].tx); f(r * 5 + 3, s.p[r].ty); f(r * 5 + 4, s.p[r].sp);
-    }
-    f(20, s.b.x); f(21, s.b.y); f(22, s.b.tx); f(23, s.b.ty); f(24, s.b.sp);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) f(25 + i, obs_elem_owner(s, i));
+    return (s.ep_step != 0 && s.owner == idx) ? 10.0 : 0.0;
 }
 
 }  // namespace futbol

@@ -2,6 +2,7 @@
 // shimming the handful of CUDA intrinsics it uses, so that the kernel's step logic can be compared with
 // the oracle on a machine without a GPU (tests/test_v0_step_host.py).  Nothing in the package loads this.
 // Built with -ffp-contract=off: every shimmed operation is one IEEE double operation, as on the device.
+// One "lane": the shared-memory columns of the device layout collapse to a plain array (FUTBOL_LANES = 1).
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -9,7 +10,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __noinline__
-#define FUTBOL_ENV_THREADS 1
+#define FUTBOL_LANES 1
 #define FUTBOL_HOST_SHIM 1
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
@@ -34,31 +35,32 @@ void host_v0_rollout(uint64_t seed, uint32_t env_id0, int random_opp, int one_go
                      double *obs, double *reward, uint8_t *done, uint8_t *flags)
 {
     V0Params P;
-    P.seed = seed; P.key = philox_expand_key(seed); P.env_id_offset = env_id0; P.n_envs = n; P.random_opp = random_opp; P.one_goal_end = one_goal_end;
-    P.only_reward_goal = only_reward_goal; P.auto_reset = auto_reset; P.ep_limit = ep_limit; P.shoot_speed = shoot_speed;
-    P.player_speed = player_speed; P.reach_sq_max = reach_sq_max;
-    uint32_t draws[kPreDraws];
+    P.seed = seed; P.key = philox_expand_key(seed); P.env_id_offset = env_id0; P.n_envs = n; P.random_opp = random_opp;
+    P.one_goal_end = one_goal_end; P.only_reward_goal = only_reward_goal; P.auto_reset = auto_reset; P.ep_limit = ep_limit;
+    P.shoot_speed = shoot_speed; P.player_speed = player_speed; P.reach_sq_max = reach_sq_max;
+    const Lane L = make_lane(0, 0);
     for (int i = 0; i < n; ++i) {
-        V0State s;
+        V0Regs s;
         FutbolV0EnvState &e = envs[i];
-        for (int r = 0; r < 4; ++r) s.p[r] = Row{e.rows[r][0], e.rows[r][1], e.rows[r][2], e.rows[r][3], e.rows[r][4]};
-        s.b = Row{e.rows[4][0], e.rows[4][1], e.rows[4][2], e.rows[4][3], e.rows[4][4]};
+        for (int k = 0; k < 25; ++k) L.f(k * kLanes) = e.rows[k / 5][k % 5];
         s.t_total = e.t_total; s.ep_step = e.ep_step; s.ai_score = e.ai_score; s.opp_score = e.opp_score;
         s.owner = e.owner; s.last_owner = e.last_owner;
         int last_flags = e.flags;
         for (int k = 0; k < steps; ++k) {
             const size_t slot = (size_t)k * n + i;
-            const StepResult r = random_opp ? v0_step<true>(s, P, env_id0 + (uint32_t)i, actions[slot] & 15, draws)
-                                            : v0_step<false>(s, P, env_id0 + (uint32_t)i, actions[slot] & 15, draws);
+            const StepResult r = random_opp ? v0_step<true>(L, s, P, env_id0 + (uint32_t)i, actions[slot] & 15)
+                                            : v0_step<false>(L, s, P, env_id0 + (uint32_t)i, actions[slot] & 15);
             last_flags = r.flags;
-            if (r.done && auto_reset) reset_env(s);
-            if (obs) for_each_obs(s, [&](int j, double v) { obs[slot * 30 + j] = v; });
+            if (r.done && auto_reset) reset_env(L, s);
+            if (obs) {
+                for (int j = 0; j < 25; ++j) obs[slot * 30 + j] = L.f(j * kLanes);
+                for (int j = 0; j < 5; ++j) obs[slot * 30 + 25 + j] = obs_owner_elem(s, j);
+            }
             if (reward) reward[slot] = r.reward;
             if (done) done[slot] = (uint8_t)r.done;
             if (flags) flags[slot] = (uint8_t)r.flags;
         }
-        for (int r = 0; r < 4; ++r) { e.rows[r][0] = s.p[r].x; e.rows[r][1] = s.p[r].y; e.rows[r][2] = s.p[r].tx; e.rows[r][3] = s.p[r].ty; e.rows[r][4] = s.p[r].sp; }
-        e.rows[4][0] = s.b.x; e.rows[4][1] = s.b.y; e.rows[4][2] = s.b.tx; e.rows[4][3] = s.b.ty; e.rows[4][4] = s.b.sp;
+        for (int k = 0; k < 25; ++k) e.rows[k / 5][k % 5] = L.f(k * kLanes);
         e.t_total = s.t_total; e.ep_step = s.ep_step; e.ai_score = s.ai_score; e.opp_score = s.opp_score;
         e.owner = (uint8_t)s.owner; e.last_owner = (uint8_t)s.last_owner; e.flags = (uint8_t)last_flags;
     }
