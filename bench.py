@@ -26,10 +26,23 @@ if ROOT not in sys.path:
 
 TOTAL_ENVS = 1 << 20
 ROLLOUT_K = 64
+E2E_CHUNKS = 8                                 # launches per step in the end-to-end loop (copy/compute overlap)
 STATE_BYTES_PER_ENV = 223                      # SoA state, v0_kernels.cu
 BYTES_PER_ENV_STEP = 120 + 4 + 1 + 1 + 2.0 * STATE_BYTES_PER_ENV / ROLLOUT_K   # obs f32x30, reward, done, action, state/K
 METRIC = "env-steps/sec (whole box) 2v2 at 2^20 envs"
 UNIT = "env-steps/s"
+
+
+def measured_traffic(n_local, K):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch of this size, from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            for rec in json.load(f)["launches"]:
+                if rec["envs"] == n_local and rec["K"] == K:
+                    return rec["dram_bytes"]
+    except Exception:  # noqa: BLE001
+        pass
+    return None
 
 
 def measured_peaks():
@@ -224,10 +237,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    assert args.envs % world == 0
-    n_local = args.envs // world
+    from gym_futbol_b200.sharding import shard
+    assert args.envs % world == 0, "the metric's env count must split evenly over the ranks"
+    first_env, n_local = shard(args.envs, rank, world)
     K = ROLLOUT_K
-    env = FutbolVecEnv(n_local, device=dev, seed=0, env_id_offset=rank * n_local, random_opp=bool(args.random_opp))
+    env = FutbolVecEnv(n_local, device=dev, seed=0, env_id_offset=first_env, random_opp=bool(args.random_opp))
     env.reset()
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
     acts = torch.randint(0, 16, (K, n_local), dtype=torch.uint8, device=dev, generator=g)   # resident in HBM
@@ -266,34 +280,85 @@ def main():
     value = args.envs * K * args.steps / (elapsed_ms * 1e-3)
 
     # ---- end to end through the public API with HOST buffers (`e2e`) ----
+    # What a host-side consumer of the reference API gets: actions come from pinned host memory, and every
+    # observation, reward and done flag of the step is delivered back into pinned host memory.  The K = 64
+    # rollout is issued as E2E_CHUNKS launches of K / E2E_CHUNKS steps so that the device->host copy of one
+    # chunk (copy stream) overlaps the simulation of the next (compute stream); two device buffers alternate.
+    chunks = E2E_CHUNKS
+    Kc = K // chunks
     h_acts = torch.randint(0, 16, (K, n_local), dtype=torch.uint8).pin_memory()
-    d_acts = torch.empty_like(acts)
+    h_obs = torch.empty((K, n_local, 30), dtype=torch.float32).pin_memory()
     h_rew = torch.empty((K, n_local), dtype=torch.float32).pin_memory()
     h_done = torch.empty((K, n_local), dtype=torch.uint8).pin_memory()
     h_stats = torch.empty(64, dtype=torch.uint8).pin_memory()
+    d_bufs = [(torch.empty((Kc, n_local), dtype=torch.uint8, device=dev),
+               torch.empty((Kc, n_local, 30), dtype=torch.float32, device=dev),
+               torch.empty((Kc, n_local), dtype=torch.float32, device=dev),
+               torch.empty((Kc, n_local), dtype=torch.uint8, device=dev)) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
+    ev_done = [torch.cuda.Event() for _ in range(2)]      # chunk simulated (compute stream)
+    ev_free = [torch.cuda.Event() for _ in range(2)]      # chunk copied out (copy stream)
 
     def e2e_step():
-        d_acts.copy_(h_acts, non_blocking=True)
-        _, rew, done = env.rollout(K, actions=d_acts)
-        h_rew.copy_(rew, non_blocking=True)
-        h_done.copy_(done, non_blocking=True)
-        h_stats.copy_(env.stats, non_blocking=True)
-        stream.synchronize()                     # the host consumer needs this step's result before the next one
+        for c in range(chunks):
+            b = c & 1
+            da, do, dr, dd = d_bufs[b]
+            ks = slice(c * Kc, (c + 1) * Kc)
+            stream.wait_event(ev_free[b])
+            da.copy_(h_acts[ks], non_blocking=True)
+            env.rollout(Kc, actions=da, out=(do, dr, dd))
+            ev_done[b].record(stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_done[b])
+                h_obs[ks].copy_(do, non_blocking=True)
+                h_rew[ks].copy_(dr, non_blocking=True)
+                h_done[ks].copy_(dd, non_blocking=True)
+                ev_free[b].record(copy_stream)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_done[(chunks - 1) & 1])
+            h_stats.copy_(env.stats, non_blocking=True)
+        copy_stream.synchronize()                # the host consumer holds the whole step before the next begins
 
-    for _ in range(3):
+    for b in range(2):
+        ev_free[b].record(copy_stream)
+    for _ in range(2):
         e2e_step()
     barrier()
+    e2e_steps = max(2, min(args.steps, 5))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(3, min(args.steps, 10))
     e0.record(stream)
     for _ in range(e2e_steps):
         e2e_step()
-    e1.record(stream)
+    e1.record(copy_stream)                       # the last device->host copy of the last step ends here
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = args.envs * K * e2e_steps / (t.item() * 1e-3)
+    e2e_launches = chunks * e2e_steps
+
+    # the same loop with observations left in HBM for an on-device policy (the zero-copy use north_star describes)
+    def resident_step():
+        da = d_bufs[0][0]
+        for c in range(chunks):
+            da.copy_(h_acts[c * Kc:(c + 1) * Kc], non_blocking=True)
+            env.rollout(Kc, actions=da)
+        h_stats.copy_(env.stats, non_blocking=True)
+        stream.synchronize()
+
+    for _ in range(2):
+        resident_step()
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record(stream)
+    for _ in range(e2e_steps):
+        resident_step()
+    r1.record(stream)
+    barrier()
+    t = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    resident_value = args.envs * K * e2e_steps / (t.item() * 1e-3)
 
     stats = torch.from_numpy(env.stats.cpu().numpy().view("int64").copy()).to(dev)   # optional statistics gather
     if world > 1:
@@ -313,15 +378,22 @@ def main():
                        "l2": "each step writes %.2f GB per GPU (obs/reward/done), larger than the 126 MB L2"
                              % (n_local * K * 125 / 1e9)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_acts.numel()) * world,
-                    "d2h_bytes_per_step": int(h_rew.numel() * 4 + h_done.numel() + 64) * world,
-                    "note": "pinned-host actions in; reward, done and statistics out; observations stay in HBM for "
-                            "the policy (zero-copy) by design"},
-            "gpu_launches": int(launches),
+                    "d2h_bytes_per_step": int(h_obs.numel() * 4 + h_rew.numel() * 4 + h_done.numel() + 64) * world,
+                    "launches_per_step": chunks,
+                    "note": "pinned-host actions in; EVERY observation, reward and done flag of the step copied back to "
+                            "pinned host memory (PCIe-bound), copy of chunk c overlapped with simulation of chunk c+1",
+                    "obs_resident_in_hbm": {"value": resident_value, "unit": UNIT,
+                                            "note": "same loop, observations consumed on the device (zero-copy policy): "
+                                                    "host actions in, statistics out"}},
+            "gpu_launches": int(launches), "gpu_launches_e2e": int(e2e_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "v0_rollout_kernel",
+                         "traffic": measured_traffic(n_local, K), "peak_source": peak_src, "kernel": "v0_rollout_kernel",
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": kernel_ms,
-                         "note": "instruction-issue bound (fp64 sqrt/div, divergent action branches), see profiles/"},
+                         "algorithmic_bytes_per_launch": n_local * K * BYTES_PER_ENV_STEP,
+                         "note": "the kernel is instruction-issue bound (fp64 IEEE sqrt/div sequences, selects, Philox), "
+                                 "not HBM bound: see profiles/README.md; traffic = ncu dram bytes of one launch of this "
+                                 "size (profiles/traffic.json), null if not captured for this size"},
             "rollout_stats": {"episodes": int(stats[2]), "goals_ai": int(stats[3]), "goals_opp": int(stats[4]),
                               "out_of_field": int(stats[5])},
         }

@@ -106,26 +106,34 @@ class FutbolVecEnv:
                                             _ptr(self.dones), _ptr(self.final_obs), self._dt, self._stream()))
         return self.obs, self.rewards, self.dones, {"terminal_observation": self.final_obs}
 
-    def rollout(self, K, actions=None, obs=True, reward=True, done=True):
+    def rollout(self, K, actions=None, obs=True, reward=True, done=True, out=None):
         """K fused steps.  actions: uint8 [K, n] or None (uniform random actions drawn in-kernel).
 
-        Returns (obs [K, n, 30] f32, reward [K, n] f32, done [K, n] u8); buffers are cached per K.
+        Returns (obs [K, n, 30] f32, reward [K, n] f32, done [K, n] u8).  By default the buffers are owned by
+        this object and cached per K; ``out=(obs, reward, done)`` writes into caller-provided contiguous CUDA
+        tensors of those shapes and dtypes instead (e.g. slices of a PPO rollout buffer); an entry may be None.
         """
         K = int(K)
         n = self.num_envs
-        buf = self._roll.get(K)
-        if buf is None:
-            buf = (torch.empty((K, n, OBS_DIM_V0), dtype=torch.float32, device=self.device),
-                   torch.empty((K, n), dtype=torch.float32, device=self.device),
-                   torch.empty((K, n), dtype=torch.uint8, device=self.device))
-            self._roll[K] = buf
-        o, r, d = buf
+        if out is not None:
+            o, r, d = out
+            for t, shape, dt in ((o, (K, n, OBS_DIM_V0), torch.float32), (r, (K, n), torch.float32), (d, (K, n), torch.uint8)):
+                if t is not None and (tuple(t.shape) != shape or t.dtype != dt or t.device != self.device or not t.is_contiguous()):
+                    raise ValueError("out tensors must be contiguous %s tensors of shape %s on %s" % (dt, shape, self.device))
+        else:
+            buf = self._roll.get(K)
+            if buf is None:
+                buf = (torch.empty((K, n, OBS_DIM_V0), dtype=torch.float32, device=self.device),
+                       torch.empty((K, n), dtype=torch.float32, device=self.device),
+                       torch.empty((K, n), dtype=torch.uint8, device=self.device))
+                self._roll[K] = buf
+            o, r, d = buf
+            o, r, d = (o if obs else None), (r if reward else None), (d if done else None)
         with torch.cuda.device(self.device):
             a = None if actions is None else self._actions(actions, (K, n))
-            _lib.check(self.lib.futbol_rollout(self._h, _ptr(self.state), K, _ptr(a), _ptr(o if obs else None),
-                                               _ptr(r if reward else None), _ptr(d if done else None),
+            _lib.check(self.lib.futbol_rollout(self._h, _ptr(self.state), K, _ptr(a), _ptr(o), _ptr(r), _ptr(d),
                                                _ptr(self.stats), self._stream()))
-        return (o if obs else None), (r if reward else None), (d if done else None)
+        return o, r, d
 
     # ------------------------------------------------------------------ state / statistics
     def get_state(self):
