@@ -295,7 +295,7 @@ __device__ __forceinline__ void player_turn(Lane L, uint32_t &j, V0Regs &s, cons
 }
 
 // defence_near (:280-289, with the stale-view behaviour Q1) + screw_vec (:101-116) for the pending kick.
-// By specification (oracle/philox.py) a step's normal() call consumes no sequential draws: slot k lives in
+// By specification a step's normal() call consumes no sequential draws: slot k lives in
 // Philox block 0x8000 + (k >> 1), words 2(k&1), 2(k&1)+1, so only the block of the picked slot is evaluated.
 __device__ __forceinline__ void resolve_shot(Lane L, const V0Regs &s, const V0Params &P, bool random_opp, uint32_t env_id,
                                              const PendingShot &shot)
