@@ -34,6 +34,8 @@ class FutbolStats(C.Structure):
 V0_ENV_STATE = np.dtype([("rows", np.float64, (5, 5)), ("t_total", np.uint64), ("ep_step", np.int32),
                          ("ai_score", np.int32), ("opp_score", np.int32), ("owner", np.uint8),
                          ("last_owner", np.uint8), ("flags", np.uint8), ("pad_", np.uint8)], align=True)
+V1_ENV_STATE = np.dtype([("body", np.float64, (21, 6)), ("t_total", np.uint64), ("stamp", np.uint32), ("ep_step", np.int32),
+                         ("owner_side", np.uint8), ("flags", np.uint8), ("pad_", np.uint8, (2,))], align=True)
 STATS_DTYPE = np.dtype([("reward_sum", np.float64), ("env_steps", np.uint64), ("episodes", np.uint64),
                         ("goals_ai", np.uint64), ("goals_opp", np.uint64), ("out_of_field", np.uint64),
                         ("reserved", np.uint64, (2,))])

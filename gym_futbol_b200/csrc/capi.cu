@@ -7,12 +7,15 @@
 #include <new>
 #include "../../include/futbol_b200.h"
 #include "v0_kernels.h"
+#include "v1_kernels.h"
 
 using namespace futbol;
 
 struct FutbolHandle {
     FutbolConfig cfg;
     V0Params v0;
+    v1::V1Params v1;
+    bool is_v1;
     uint64_t launches;
     bool initialised;   // first futbol_reset zeroes t_total
 };
@@ -38,6 +41,35 @@ static int episode_limit(double game_time)
     return k;
 }
 
+// v1: `current_time += 0.1; done = current_time > total_time` (envs_v1/futbol_env.py:478-481): the step count
+// at which done first holds (300 for total_time = 30: the float sum of 300 x 0.1 is 30.000000000000156).
+static int episode_limit_v1(double total_time)
+{
+    double t = 0.0;
+    int k = 0;
+    do { t += 0.1; ++k; } while (!(t > total_time) && k < (1 << 30));
+    return k;
+}
+
+// kick-off formation of one side, envs_v1/team.py:52-112 (Python float arithmetic, left to right)
+static void formation_v1(int n, bool right, double *xs, double *ys)
+{
+    const double w = 105.0, h = 68.0;
+    if (n <= 3) {
+        for (int i = 0; i < n; ++i) { xs[i] = right ? w * 0.75 : w * 0.25; ys[i] = (h / (n + 1)) * (i + 1); }
+    } else if (n <= 6) {
+        for (int i = 0; i < n; ++i) xs[i] = i < 3 ? (right ? w * 5 / 6 : w * 1 / 6) : (right ? w * 4 / 6 : w * 2 / 6);
+        for (int i = 0; i < 3; ++i) ys[i] = (h / (3 + 1)) * (i + 1);
+        for (int i = 0; i < n - 3; ++i) ys[3 + i] = (h / (n - 3 + 1)) * (i + 1);
+    } else {
+        for (int i = 0; i < n; ++i)
+            xs[i] = i < 4 ? (right ? w * 7 / 8 : w * 1 / 8) : (i < 7 ? (right ? w * 6 / 8 : w * 2 / 8) : (right ? w * 5 / 8 : w * 3 / 8));
+        for (int i = 0; i < 4; ++i) ys[i] = (h / (4 + 1)) * (i + 1);
+        for (int i = 0; i < 3; ++i) ys[4 + i] = (h / (3 + 1)) * (i + 1);
+        for (int i = 0; i < n - 7; ++i) ys[7 + i] = (h / (n - 7 + 1)) * (i + 1);
+    }
+}
+
 // Largest double s with sqrt(s) < r (IEEE sqrt is correctly rounded, hence monotone), or -1 if none:
 // lets the kernel test `sqrt(s) < r` as `s <= bound` without taking the root.
 static double sqrt_less_than_bound(double r)
@@ -59,10 +91,16 @@ int futbol_create(const FutbolConfig *cfg, FutbolHandle **out)
     if (cfg == nullptr || out == nullptr) return fail(FUTBOL_ERR_ARG, "null argument%s");
     if (cfg->abi_version != FUTBOL_ABI_VERSION) return fail(FUTBOL_ERR_ARG, "abi_version mismatch%s");
     if (cfg->n_envs <= 0) return fail(FUTBOL_ERR_ARG, "n_envs must be positive%s");
-    if (cfg->variant != FUTBOL_VARIANT_V0) return fail(FUTBOL_ERR_UNSUPPORTED, "variant not built: %s", "v1");
-    if (cfg->n_players != 2) return fail(FUTBOL_ERR_ARG, "v0 is 2v2: n_players must be 2%s");
-    if (!(cfg->game_time >= 0.0) || !(cfg->player_speed >= 0.0) || cfg->shoot_speed < 16)
-        return fail(FUTBOL_ERR_ARG, "bad game_time / player_speed / shoot_speed%s");
+    const bool is_v1 = cfg->variant == FUTBOL_VARIANT_V1;
+    if (cfg->variant != FUTBOL_VARIANT_V0 && !is_v1) return fail(FUTBOL_ERR_UNSUPPORTED, "unknown variant%s");
+    if (!is_v1) {
+        if (cfg->n_players != 2) return fail(FUTBOL_ERR_ARG, "v0 is 2v2: n_players must be 2%s");
+        if (!(cfg->game_time >= 0.0) || !(cfg->player_speed >= 0.0) || cfg->shoot_speed < 16)
+            return fail(FUTBOL_ERR_ARG, "bad game_time / player_speed / shoot_speed%s");
+    } else {
+        if (cfg->n_players < 1 || cfg->n_players > v1::kMaxN) return fail(FUTBOL_ERR_ARG, "v1: n_players must be 1..10%s");
+        if (!(cfg->game_time >= 0.0)) return fail(FUTBOL_ERR_ARG, "bad total_time%s");
+    }
     int dev_count = 0;
     cudaError_t e = cudaGetDeviceCount(&dev_count);
     if (e != cudaSuccess || dev_count == 0)
@@ -72,6 +110,22 @@ int futbol_create(const FutbolConfig *cfg, FutbolHandle **out)
     h->cfg = *cfg;
     h->launches = 0;
     h->initialised = false;
+    h->is_v1 = is_v1;
+    if (is_v1) {
+        v1::V1Params &Q = h->v1;
+        memset(&Q, 0, sizeof(Q));
+        Q.seed = cfg->seed;
+        Q.key = philox_expand_key(cfg->seed);
+        Q.env_id_offset = cfg->env_id_offset;
+        Q.n_envs = cfg->n_envs;
+        Q.n_players = cfg->n_players;
+        Q.ep_limit = episode_limit_v1(cfg->game_time);
+        Q.auto_reset = cfg->auto_reset != 0;
+        Q.damping_dt = pow(0.95, 0.1);                               // space.damping ** TIME_STEP
+        Q.bias_coef = 1.0 - pow(pow(1.0 - 0.1, 60.0), 0.1);          // Chipmunk's default collision_bias
+        formation_v1(cfg->n_players, false, Q.form_x, Q.form_y);
+        formation_v1(cfg->n_players, true, Q.form_x + cfg->n_players, Q.form_y + cfg->n_players);
+    }
     V0Params &P = h->v0;
     P.seed = cfg->seed;
     P.key = philox_expand_key(cfg->seed);
@@ -95,11 +149,15 @@ int futbol_destroy(FutbolHandle *h)
     return FUTBOL_OK;
 }
 
-size_t futbol_state_bytes(const FutbolHandle *h) { return h ? v0_state_bytes(h->cfg.n_envs) : 0; }
-size_t futbol_env_state_bytes(const FutbolHandle *h) { return h ? sizeof(FutbolV0EnvState) : 0; }
-int futbol_obs_dim(const FutbolHandle *h) { return h ? 30 : 0; }
-int futbol_act_dim(const FutbolHandle *h) { return h ? 1 : 0; }
-int futbol_draw_limit_steps(const FutbolHandle *h) { return h ? h->v0.ep_limit + 1 : 0; }
+size_t futbol_state_bytes(const FutbolHandle *h)
+{
+    if (!h) return 0;
+    return h->is_v1 ? v1::state_bytes(h->cfg.n_envs, h->cfg.n_players) : v0_state_bytes(h->cfg.n_envs);
+}
+size_t futbol_env_state_bytes(const FutbolHandle *h) { return h ? (h->is_v1 ? sizeof(FutbolV1EnvState) : sizeof(FutbolV0EnvState)) : 0; }
+int futbol_obs_dim(const FutbolHandle *h) { return h ? (h->is_v1 ? v1::obs_dim(h->cfg.n_players) : 30) : 0; }
+int futbol_act_dim(const FutbolHandle *h) { return h ? (h->is_v1 ? 2 * h->cfg.n_players : 1) : 0; }
+int futbol_draw_limit_steps(const FutbolHandle *h) { return h ? (h->is_v1 ? h->v1.ep_limit : h->v0.ep_limit + 1) : 0; }
 uint64_t futbol_launch_count(const FutbolHandle *h) { return h ? h->launches : 0; }
 
 int futbol_reset(FutbolHandle *h, void *state, const uint8_t *mask, void *obs, int obs_dtype, void *stream)
@@ -108,7 +166,8 @@ int futbol_reset(FutbolHandle *h, void *state, const uint8_t *mask, void *obs, i
     if (obs_dtype != 0 && obs_dtype != 1) return fail(FUTBOL_ERR_ARG, "obs_dtype must be 0 (f32) or 1 (f64)%s");
     const int init = (!h->initialised && mask == nullptr) ? 1 : 0;
     if (!h->initialised && mask != nullptr) return fail(FUTBOL_ERR_ARG, "first reset must cover all envs (mask = NULL)%s");
-    cudaError_t e = v0_launch_reset(h->v0, state, mask, obs, obs_dtype, init, (cudaStream_t)stream);
+    cudaError_t e = h->is_v1 ? v1::launch_reset(h->v1, state, mask, obs, obs_dtype, init, (cudaStream_t)stream)
+                             : v0_launch_reset(h->v0, state, mask, obs, obs_dtype, init, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     h->initialised = true;
     h->launches += 1;
@@ -121,7 +180,8 @@ int futbol_step(FutbolHandle *h, void *state, const uint8_t *actions, void *obs,
     if (h == nullptr || state == nullptr || actions == nullptr) return fail(FUTBOL_ERR_ARG, "null handle/state/actions%s");
     if (out_dtype != 0 && out_dtype != 1) return fail(FUTBOL_ERR_ARG, "out_dtype must be 0 (f32) or 1 (f64)%s");
     if (!h->initialised) return fail(FUTBOL_ERR_ARG, "futbol_reset must be called before futbol_step%s");
-    cudaError_t e = v0_launch_step(h->v0, state, actions, obs, reward, done, final_obs, out_dtype, (cudaStream_t)stream);
+    cudaError_t e = h->is_v1 ? v1::launch_step(h->v1, state, actions, obs, reward, done, final_obs, out_dtype, (cudaStream_t)stream)
+                             : v0_launch_step(h->v0, state, actions, obs, reward, done, final_obs, out_dtype, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     h->launches += 1;
     return FUTBOL_OK;
@@ -133,7 +193,8 @@ int futbol_rollout(FutbolHandle *h, void *state, int K, const uint8_t *actions, 
     if (h == nullptr || state == nullptr) return fail(FUTBOL_ERR_ARG, "null handle/state%s");
     if (K <= 0) return fail(FUTBOL_ERR_ARG, "K must be positive%s");
     if (!h->initialised) return fail(FUTBOL_ERR_ARG, "futbol_reset must be called before futbol_rollout%s");
-    cudaError_t e = v0_launch_rollout(h->v0, state, K, actions, obs, reward, done, stats, (cudaStream_t)stream);
+    cudaError_t e = h->is_v1 ? v1::launch_rollout(h->v1, state, K, actions, obs, reward, done, stats, (cudaStream_t)stream)
+                             : v0_launch_rollout(h->v0, state, K, actions, obs, reward, done, stats, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     h->launches += 1;
     return FUTBOL_OK;
@@ -142,7 +203,8 @@ int futbol_rollout(FutbolHandle *h, void *state, int K, const uint8_t *actions, 
 int futbol_get_state(FutbolHandle *h, const void *state, void *aos_out, void *stream)
 {
     if (h == nullptr || state == nullptr || aos_out == nullptr) return fail(FUTBOL_ERR_ARG, "null argument%s");
-    cudaError_t e = v0_launch_get_state(h->cfg.n_envs, state, aos_out, (cudaStream_t)stream);
+    cudaError_t e = h->is_v1 ? v1::launch_get_state(h->cfg.n_envs, h->cfg.n_players, state, aos_out, (cudaStream_t)stream)
+                             : v0_launch_get_state(h->cfg.n_envs, state, aos_out, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     h->launches += 1;
     return FUTBOL_OK;
@@ -151,6 +213,7 @@ int futbol_get_state(FutbolHandle *h, const void *state, void *aos_out, void *st
 int futbol_set_state(FutbolHandle *h, void *state, const void *aos_in, void *stream)
 {
     if (h == nullptr || state == nullptr || aos_in == nullptr) return fail(FUTBOL_ERR_ARG, "null argument%s");
+    if (h->is_v1) return fail(FUTBOL_ERR_UNSUPPORTED, "futbol_set_state is not available for the v1 variant%s");
     cudaError_t e = v0_launch_set_state(h->cfg.n_envs, state, aos_in, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     h->initialised = true;

@@ -1,0 +1,265 @@
+// v1 kernels (N-vs-N rigid-body variant): reset, per-step, fused K-step rollout, state export.
+//
+// HBM layout of the state buffer (structure of arrays over environments, `np` = n_envs rounded up to 256),
+// B = 2N + 1 bodies, P = B(B-1)/2 + 12 B shape pairs:
+//   double  body[6 B][np]   per body x, y, vx, vy, v_bias_x, v_bias_y (team A, team B, ball)
+//   uint64  t_total[np];  uint32 stamp[np];  int32 ep_step[np];  uint8 owner_side[np], flags[np]
+//   double  jn[P][np];  uint32 last[P][np]    the arbiter cache: accumulated normal impulse and the stamp of
+//                                             the space step in which the pair last touched
+// Inside a kernel the 6 B doubles sit in shared memory (one column per lane), scalars in registers; the
+// arbiter cache stays in HBM and is touched only by pairs in contact.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/futbol_b200.h"
+#include "v1_step.cuh"
+#include "v1_kernels.h"
+
+namespace futbol {
+namespace v1 {
+
+struct StateView {
+    double *body; uint64_t *t_total; uint32_t *stamp; int32_t *ep_step; uint8_t *owner_side, *flags; double *jn; uint32_t *last;
+    size_t np;
+};
+
+__host__ __device__ inline size_t padded(int n) { return ((size_t)n + 255) & ~(size_t)255; }
+
+size_t state_bytes(int n_envs, int n_players)
+{
+    const size_t B = 2 * n_players + 1, P = n_pairs((int)B);
+    return padded(n_envs) * (6 * B * 8 + 8 + 4 + 4 + 1 + 1 + P * 12);
+}
+
+__host__ __device__ inline StateView make_view(void *base, int n, int n_players)
+{
+    const size_t B = 2 * n_players + 1, P = n_pairs((int)B);
+    StateView v;
+    v.np = padded(n);
+    char *p = (char *)base;
+    v.body = (double *)p;        p += v.np * 6 * B * 8;
+    v.jn = (double *)p;          p += v.np * P * 8;
+    v.t_total = (uint64_t *)p;   p += v.np * 8;
+    v.last = (uint32_t *)p;      p += v.np * P * 4;
+    v.stamp = (uint32_t *)p;     p += v.np * 4;
+    v.ep_step = (int32_t *)p;    p += v.np * 4;
+    v.owner_side = (uint8_t *)p; p += v.np;
+    v.flags = (uint8_t *)p;
+    return v;
+}
+
+__device__ __forceinline__ void load_state(const StateView &v, int i, Lane L, V1Regs &s, int B)
+{
+    for (int k = 0; k < 6 * B; ++k) L.f(k * kLanes) = v.body[(size_t)k * v.np + i];
+    s.t_total = v.t_total[i]; s.stamp = v.stamp[i]; s.ep_step = v.ep_step[i]; s.owner_side = v.owner_side[i];
+}
+
+__device__ __forceinline__ void store_state(const StateView &v, int i, Lane L, const V1Regs &s, int B, int flags)
+{
+    for (int k = 0; k < 6 * B; ++k) v.body[(size_t)k * v.np + i] = L.f(k * kLanes);
+    v.t_total[i] = s.t_total; v.stamp[i] = s.stamp; v.ep_step[i] = s.ep_step; v.owner_side[i] = (uint8_t)s.owner_side;
+    v.flags[i] = (uint8_t)flags;
+}
+
+template <typename T>
+__device__ __forceinline__ void thread_store_obs(T *dst_row, Lane L, int N)
+{
+    const int D = obs_dim(N);
+    for (int k = 0; k < D; ++k) dst_row[k] = (T)obs_elem(L, N, k);
+}
+
+// fp32 observation rows staged per warp and written as consecutive 128-bit stores (a warp's 32 rows are one
+// contiguous span of [n, D])
+__device__ __forceinline__ void warp_store_obs_f32(Lane L, int N, float *stage, float *gdst_warp_row0, int lane, int rows_in_warp, bool vec_ok)
+{
+    const int D = obs_dim(N);
+    __syncwarp();
+    float *mine = stage + lane * D;
+    for (int k = 0; k < D; ++k) mine[k] = (float)obs_elem(L, N, k);
+    __syncwarp();
+    const int total = rows_in_warp * D;
+    if (vec_ok) {
+        const int nvec = total >> 2;
+        const float4 *src = reinterpret_cast<const float4 *>(stage);
+        float4 *dst = reinterpret_cast<float4 *>(gdst_warp_row0);
+        for (int q = lane; q < nvec; q += 32) __stcs(dst + q, src[q]);
+    } else {
+        for (int q = lane; q < total; q += 32) __stcs(gdst_warp_row0 + q, stage[q]);
+    }
+    __syncwarp();
+}
+
+template <typename T>
+__global__ void v1_reset_kernel(V1Params P, StateView v, const uint8_t *mask, T *obs, int init)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_envs) return;
+    if (mask != nullptr && mask[i] == 0) return;
+    const int N = P.n_players, B = 2 * N + 1;
+    const Lane L = make_lane(threadIdx.x >> 5, threadIdx.x & 31, N);
+    const uint32_t env_id = P.env_id_offset + (uint32_t)i;
+    V1Regs s;
+    if (init) init_env(L, s, P, env_id);
+    else { load_state(v, i, L, s, B); reset_env(L, s, P, env_id); }
+    store_state(v, i, L, s, B, 0);
+    if (obs != nullptr) thread_store_obs(obs + (size_t)i * obs_dim(N), L, N);
+}
+
+template <typename T>
+__global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, T *obs, T *reward, uint8_t *done, T *final_obs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_envs) return;
+    const int N = P.n_players, B = 2 * N + 1, D = obs_dim(N);
+    const Lane L = make_lane(threadIdx.x >> 5, threadIdx.x & 31, N);
+    const uint32_t env_id = P.env_id_offset + (uint32_t)i;
+    const PairCache C{v.jn + i, v.last + i, v.np};
+    Contact con[kMaxContacts];
+    V1Regs s;
+    load_state(v, i, L, s, B);
+    const StepResult r = v1_step(L, s, P, env_id, actions + (size_t)i * 2 * N, C, con);
+    if (r.done && P.auto_reset) {
+        if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * D, L, N);
+        reset_env(L, s, P, env_id);
+    }
+    store_state(v, i, L, s, B, r.flags);
+    if (obs != nullptr) thread_store_obs(obs + (size_t)i * D, L, N);
+    if (reward != nullptr) reward[i] = (T)r.reward;
+    if (done != nullptr) done[i] = (uint8_t)r.done;
+}
+
+__global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t *__restrict__ actions, float *__restrict__ obs,
+                                  float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_env0 = i - lane;
+    if (warp_env0 >= P.n_envs) return;
+    const bool live = i < P.n_envs;
+    const int rows_in_warp = min(32, P.n_envs - warp_env0);
+    const int N = P.n_players, B = 2 * N + 1, D = obs_dim(N);
+    const size_t n = (size_t)P.n_envs;
+    const bool vec_ok = ((n * D) % 4 == 0) && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0) && rows_in_warp == 32;
+    const uint32_t env_id = P.env_id_offset + (uint32_t)i;
+    const Lane L = make_lane(warp, lane, N);
+    float *stage = reinterpret_cast<float *>(futbol_smem + warp * warp_smem_bytes(N) + warp_state_bytes(N));
+    // padding lanes of the last warp step env 0's cache column?  No: they get a private dummy state and never touch HBM
+    const int ci = live ? i : 0;
+    const PairCache C{v.jn + ci, v.last + ci, v.np};
+    Contact con[kMaxContacts];
+
+    V1Regs s;
+    if (live) load_state(v, i, L, s, B);
+    else init_env(L, s, P, env_id);
+
+    double reward_sum = 0.0;
+    uint32_t episodes = 0, goals_l = 0, goals_r = 0, outs = 0, contacts = 0, overflow = 0;
+    int last_flags = 0;
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+        const size_t slot = (size_t)k * n + (size_t)i;
+        StepResult r;
+        if (live) {
+            r = v1_step(L, s, P, env_id, actions != nullptr ? actions + slot * 2 * N : nullptr, C, con);
+            if (r.done && P.auto_reset) reset_env(L, s, P, env_id);
+        } else {
+            r.reward = 0.0; r.done = 0; r.flags = 0; r.contacts = 0; r.overflow = 0;
+        }
+        last_flags = r.flags;
+        reward_sum += r.reward;
+        goals_l += (r.flags & kFlagGoalLeft) != 0;
+        goals_r += (r.flags & kFlagGoal) && !(r.flags & kFlagGoalLeft);
+        outs += (r.flags & kFlagOut) != 0;
+        episodes += r.done;
+        contacts += r.contacts; overflow += r.overflow;
+        if (obs != nullptr) warp_store_obs_f32(L, N, stage, obs + ((size_t)k * n + (size_t)warp_env0) * D, lane, rows_in_warp, vec_ok);
+        if (live) {
+            if (reward != nullptr) __stcs(reward + slot, (float)r.reward);
+            if (done != nullptr) done[slot] = (uint8_t)r.done;
+        }
+    }
+    if (live) store_state(v, i, L, s, B, last_flags);
+
+    if (stats != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            reward_sum += __shfl_xor_sync(0xffffffffu, reward_sum, o);
+            episodes += __shfl_xor_sync(0xffffffffu, episodes, o);
+            goals_l += __shfl_xor_sync(0xffffffffu, goals_l, o);
+            goals_r += __shfl_xor_sync(0xffffffffu, goals_r, o);
+            outs += __shfl_xor_sync(0xffffffffu, outs, o);
+            contacts += __shfl_xor_sync(0xffffffffu, contacts, o);
+            overflow += __shfl_xor_sync(0xffffffffu, overflow, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&stats->reward_sum, reward_sum);
+            atomicAdd((unsigned long long *)&stats->env_steps, (unsigned long long)rows_in_warp * (unsigned long long)K);
+            atomicAdd((unsigned long long *)&stats->episodes, (unsigned long long)episodes);
+            atomicAdd((unsigned long long *)&stats->goals_ai, (unsigned long long)goals_l);
+            atomicAdd((unsigned long long *)&stats->goals_opp, (unsigned long long)goals_r);
+            atomicAdd((unsigned long long *)&stats->out_of_field, (unsigned long long)outs);
+            atomicAdd((unsigned long long *)&stats->reserved[0], (unsigned long long)contacts);
+            atomicAdd((unsigned long long *)&stats->reserved[1], (unsigned long long)overflow);
+        }
+    }
+}
+
+__global__ void v1_get_state_kernel(int n, int n_players, StateView v, FutbolV1EnvState *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int B = 2 * n_players + 1;
+    FutbolV1EnvState e;
+    for (int b = 0; b < 21; ++b) for (int f = 0; f < 6; ++f) e.body[b][f] = b < B ? v.body[(size_t)(6 * b + f) * v.np + i] : 0.0;
+    e.t_total = v.t_total[i]; e.stamp = v.stamp[i]; e.ep_step = v.ep_step[i]; e.owner_side = v.owner_side[i];
+    e.flags = v.flags[i]; e.pad_[0] = e.pad_[1] = 0;
+    out[i] = e;
+}
+
+// ---- host launchers ------------------------------------------------------------------------------------
+static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
+static inline int threads_for(int n_players) { return n_players <= 5 ? 64 : 32; }   // keeps a block under 48 KB of shared memory
+static inline int smem_for(int n_players) { return (threads_for(n_players) / 32) * warp_smem_bytes(n_players); }
+
+cudaError_t launch_reset(const V1Params &P, void *state, const uint8_t *mask, void *obs, int obs_f64, int init, cudaStream_t st)
+{
+    const StateView v = make_view(state, P.n_envs, P.n_players);
+    const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
+    if (init) {   // first construction: an empty arbiter cache
+        const size_t P_ = n_pairs(2 * P.n_players + 1);
+        cudaError_t e = cudaMemsetAsync(v.jn, 0, v.np * P_ * 8, st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(v.last, 0, v.np * P_ * 4, st);
+        if (e != cudaSuccess) return e;
+    }
+    if (obs_f64) v1_reset_kernel<double><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, mask, (double *)obs, init);
+    else v1_reset_kernel<float><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, mask, (float *)obs, init);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step(const V1Params &P, void *state, const uint8_t *actions, void *obs, void *reward, uint8_t *done,
+                        void *final_obs, int out_f64, cudaStream_t st)
+{
+    const StateView v = make_view(state, P.n_envs, P.n_players);
+    const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
+    if (out_f64) v1_step_kernel<double><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, actions, (double *)obs, (double *)reward, done, (double *)final_obs);
+    else v1_step_kernel<float><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, actions, (float *)obs, (float *)reward, done, (float *)final_obs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rollout(const V1Params &P, void *state, int K, const uint8_t *actions, float *obs, float *reward,
+                           uint8_t *done, FutbolStats *stats, cudaStream_t st)
+{
+    const StateView v = make_view(state, P.n_envs, P.n_players);
+    const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
+    v1_rollout_kernel<<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, K, actions, obs, reward, done, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_get_state(int n, int n_players, const void *state, void *aos, cudaStream_t st)
+{
+    v1_get_state_kernel<<<blocks_for(n, 128), 128, 0, st>>>(n, n_players, make_view(const_cast<void *>(state), n, n_players), (FutbolV1EnvState *)aos);
+    return cudaGetLastError();
+}
+
+}  // namespace v1
+}  // namespace futbol

@@ -1,0 +1,470 @@
+// Device-side v1 environment step (N-vs-N, rigid-body contacts): one thread owns one environment.
+// Replaces gym_futbol/envs_v1/futbol_env.py Futbol.step (:427-483) / reset (:145-150) with team.py,
+// player.py, ball.py, and the subset of Chipmunk2D 7 (pymunk) those files drive: cpSpaceStep with
+// circle/circle and circle/segment contacts, arbiter pre-step, damped velocity integration with the
+// reference's speed clamps, warm start, ten sequential-impulse iterations.
+//
+// PARITY UNPINNED at the pymunk boundary: the physics restates Chipmunk's published
+// algorithm; what Chipmunk leaves implementation-defined (body order, contact order, ...) is specified in
+// DESIGN.md and implemented identically by the CPU checker, with which this code agrees bit for bit.
+// Arithmetic: fp64, one IEEE operation per written operation, no FMA contraction.
+//
+// Why one thread per environment and not one warp (players on lanes): the per-environment parallelism is
+// tiny (5 to 21 bodies) and the expensive parts are sequential by construction (the 2N action turns share the
+// ball; sequential impulses are Gauss-Seidel), so lanes-as-bodies leaves most of a warp idle in exactly the
+// phases that cost the most, while environments are independent and plentiful.  Layout: the 6(2N+1) body
+// doubles in shared memory, one column per lane (run-time indexable, conflict-free); the arbiter cache
+// (accumulated impulse + step stamp per shape pair, dense, touched only by pairs in contact) in HBM; the
+// step's contact list in local memory.
+#pragma once
+#include <stdint.h>
+#include "philox.cuh"
+
+namespace futbol {
+namespace v1 {
+
+constexpr int kMaxN = 10, kMaxBodies = 2 * kMaxN + 1, kNSeg = 12, kMaxContacts = 32;
+constexpr double kWidth = 105.0, kHeight = 68.0, kGoalSize = 20.0, kDt = 0.1;      // futbol_env.py:19-26
+constexpr double kBallMaxV = 25.0, kPlayerMaxV = 10.0;                              // :31-32
+constexpr double kBallWeight = 10.0, kPlayerWeight = 20.0;                          // :34-35
+constexpr double kPlayerForce = 40.0, kBallForce = 120.0;                           // :37-38
+constexpr double kRPlayer = 1.5, kRBall = 1.0, kRSeg = 1.0, kElasticity = 0.2;      // player.py:7, ball.py:7, :187
+constexpr double kSlop = 0.1;                                                       // Chipmunk collision_slop
+enum : int { kFlagGoal = 1, kFlagOut = 2, kFlagDone = 4, kFlagGoalLeft = 8 };
+constexpr uint32_t kResetBlock = 0x4000u;   // Philox block of the side drawn by reset()
+constexpr uint32_t kStamp0 = 8;             // first space-step stamp (cache entries start at 0 = "never touched")
+
+// the 12 segments of _setup_walls (:184-224): six boundary segments, then six goal-box segments
+__device__ __forceinline__ void segment(int s, double &ax, double &ay, double &bx, double &by)
+{
+    const double lo = kHeight / 2 - kGoalSize / 2, hi = kHeight / 2 + kGoalSize / 2;
+    switch (s) {
+    case 0: ax = 0; ay = 0; bx = 0; by = lo; break;
+    case 1: ax = 0; ay = hi; bx = 0; by = kHeight; break;
+    case 2: ax = 0; ay = kHeight; bx = kWidth; by = kHeight; break;
+    case 3: ax = kWidth; ay = 0; bx = kWidth; by = lo; break;
+    case 4: ax = kWidth; ay = hi; bx = kWidth; by = kHeight; break;
+    case 5: ax = 0; ay = 0; bx = kWidth; by = 0; break;
+    case 6: ax = -2; ay = lo; bx = -2; by = hi; break;
+    case 7: ax = -2; ay = lo; bx = 0; by = lo; break;
+    case 8: ax = -2; ay = hi; bx = 0; by = hi; break;
+    case 9: ax = kWidth + 2; ay = lo; bx = kWidth + 2; by = hi; break;
+    case 10: ax = kWidth; ay = lo; bx = kWidth + 2; by = lo; break;
+    default: ax = kWidth; ay = hi; bx = kWidth + 2; by = hi; break;
+    }
+}
+
+struct V1Params {
+    uint64_t seed;
+    PhiloxKey key;
+    uint32_t env_id_offset;
+    int n_envs;
+    int n_players;        // number_of_player, :65
+    int ep_limit;         // first k with k additions of 0.1 > total_time (300 for 30), :478-481
+    int auto_reset;
+    double damping_dt;    // pow(0.95, 0.1): space.damping ** dt, :99
+    double bias_coef;     // 1 - pow(pow(0.9, 60), 0.1): Chipmunk collision_bias default
+    double form_x[2 * kMaxN], form_y[2 * kMaxN];   // kick-off formation, team.py:52-112
+};
+
+// ---- per-environment working storage --------------------------------------------------------------------
+// shared memory, one column per lane: element (6 * body + field) of lane l at st[(6 * body + field) * kLanes + l];
+// fields x, y, vx, vy, v_bias_x, v_bias_y; bodies: team A 0..N-1, team B N..2N-1, ball 2N.
+#ifndef FUTBOL_HOST_SHIM
+extern __shared__ __align__(16) unsigned char futbol_smem[];
+#else
+static unsigned char futbol_smem[8 * 6 * kMaxBodies + 4 * (4 + 8 * kMaxN)] __attribute__((aligned(16)));
+#endif
+constexpr int kPX = 0, kPY = kLanes, kVX = 2 * kLanes, kVY = 3 * kLanes, kBX = 4 * kLanes, kBY = 5 * kLanes;
+constexpr int kBodyStride = 6 * kLanes;
+
+struct Lane {
+    uint32_t st;          // index (in doubles) of this lane's element 0
+    __device__ __forceinline__ double &f(int k) const { return reinterpret_cast<double *>(futbol_smem)[st + k]; }
+};
+
+__host__ __device__ constexpr int warp_state_bytes(int n_players) { return 6 * (2 * n_players + 1) * kLanes * 8; }
+__host__ __device__ constexpr int obs_dim(int n_players) { return 4 + 8 * n_players; }
+__host__ __device__ constexpr int warp_smem_bytes(int n_players) { return warp_state_bytes(n_players) + obs_dim(n_players) * kLanes * 4; }
+__host__ __device__ constexpr int n_pairs(int bodies) { return bodies * (bodies - 1) / 2 + bodies * kNSeg; }
+
+__device__ __forceinline__ Lane make_lane(int warp_in_block, int lane, int n_players)
+{
+    Lane L;
+    L.st = (uint32_t)(warp_in_block * (warp_smem_bytes(n_players) / 8) + lane);
+    return L;
+}
+
+// the arbiter cache of this environment in HBM: pair q at jn[q * stride], last[q * stride]
+struct PairCache { double *jn; uint32_t *last; size_t stride; };
+
+// scalars (registers)
+struct V1Regs {
+    uint64_t t_total;
+    uint32_t stamp;       // space steps taken so far (0.1 steps and the 1e-4 kick-off steps), starts at kStamp0
+    int ep_step, owner_side;
+};
+
+struct Contact { double nx, ny, n_mass, bias, bounce, jn, jbias; int a, b, q; };
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
+
+__device__ __forceinline__ uint32_t philox_word(const V1Params &P, uint32_t env_id, uint32_t stream, uint64_t t, uint32_t j)
+{
+    const Philox4 p = philox_step_block(P.key, env_id, stream, t, j >> 2);
+    const uint32_t lo = (j & 1u) ? p.y : p.x, hi = (j & 1u) ? p.w : p.z;
+    return (j & 2u) ? hi : lo;
+}
+// sequential dynamics draw (stream 3): rare (pass target, out-of-bounds receiver, side after a goal)
+__device__ __forceinline__ uint32_t draw(const V1Params &P, uint32_t env_id, uint64_t t, uint32_t &j)
+{
+    const uint32_t w = philox_word(P, env_id, kStreamV1Dynamics, t, j);
+    j += 1;
+    return w;
+}
+
+// _position_to_initial, :129-143: teleport to the formation, zero velocities, space.step(1e-4).  With all
+// velocities zero the 1e-4 step only consumes the bias velocities (p += v_bias * 1e-4, v_bias = 0), finds no
+// contact (formation spacing >= 13.6) and ages the cached arbiters by one step.
+__device__ __forceinline__ void position_to_initial(Lane L, V1Regs &s, const V1Params &P)
+{
+    const int N = P.n_players, B = 2 * N + 1;
+    for (int i = 0; i < B; ++i) {
+        const int o = i * kBodyStride;
+        const double x = i < 2 * N ? P.form_x[i] : dmul(kWidth, 0.5), y = i < 2 * N ? P.form_y[i] : dmul(kHeight, 0.5);
+        L.f(o + kPX) = dadd(x, dmul(dadd(0.0, L.f(o + kBX)), 0.0001));
+        L.f(o + kPY) = dadd(y, dmul(dadd(0.0, L.f(o + kBY)), 0.0001));
+        L.f(o + kVX) = 0.0; L.f(o + kVY) = 0.0; L.f(o + kBX) = 0.0; L.f(o + kBY) = 0.0;
+    }
+    s.stamp += 1;
+}
+
+__device__ __forceinline__ void reset_env(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id)
+{   // Futbol.reset, :145-150 (t_total, the Philox step index, is deliberately kept; so is the arbiter cache)
+    s.ep_step = 0;
+    s.owner_side = (int)__umulhi(philox_step_block(P.key, env_id, kStreamV1Dynamics, s.t_total, kResetBlock).x, 2u);
+    position_to_initial(L, s, P);
+}
+
+// first construction (Futbol.__init__ -> reset): zero bias velocities, fresh stamps
+__device__ __forceinline__ void init_env(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id)
+{
+    const int B = 2 * P.n_players + 1;
+    for (int i = 0; i < B; ++i) { L.f(i * kBodyStride + kBX) = 0.0; L.f(i * kBodyStride + kBY) = 0.0; }
+    s.t_total = 0;
+    s.stamp = kStamp0;
+    reset_env(L, s, P, env_id);
+}
+
+// observation element k of the normalised vector [ball, team A, team B], :154-180
+__device__ __forceinline__ double obs_elem(Lane L, int N, int k)
+{
+    const int body = k < 4 ? 2 * N : (k - 4) >> 2, fld = k & 3;
+    const double v = L.f(body * kBodyStride + fld * kLanes);
+    const double avg = fld == 0 ? 52.5 : (fld == 1 ? 34.0 : 0.0);
+    const double rng = fld == 0 ? (k < 4 ? 52.5 : 55.5) : (fld == 1 ? 34.0 : (k < 4 ? 25.0 : 10.0));
+    return ddiv(dsub(v, avg), rng);
+}
+
+__device__ __forceinline__ bool touching(Lane L, int p, int ball)
+{   // Ball.has_contact_with, ball.py:39-40 = Chipmunk CircleToCircle: |delta|^2 < (r1 + r2)^2
+    const double dx = dsub(L.f(p * kBodyStride + kPX), L.f(ball * kBodyStride + kPX));
+    const double dy = dsub(L.f(p * kBodyStride + kPY), L.f(ball * kBodyStride + kPY));
+    return dadd(dmul(dx, dx), dmul(dy, dy)) < (kRBall + kRPlayer) * (kRBall + kRPlayer);
+}
+
+// Team.get_pass_target_teammate, team.py:136-180; returns the body index of the target
+__device__ __forceinline__ int pass_target(Lane L, const V1Params &P, uint32_t env_id, uint64_t t, uint32_t &j, int p, int arrow)
+{
+    const int N = P.n_players, base = p < N ? 0 : N, k = p - base;
+    if (N == 1) return p;                                                // :137-138
+    const uint32_t w = draw(P, env_id, t, j);                            // :141-142: any other teammate
+    const int r = (int)(((uint64_t)(w >> 8) * (uint64_t)(N - 1)) >> 24);
+    int target = r < k ? r : r + 1;
+    if (arrow != 0) {                                                    // :148-178
+        const double px = L.f(p * kBodyStride + kPX), py = L.f(p * kBodyStride + kPY);
+        uint32_t elig = 0;
+        for (int i = 0; i < N; ++i) {
+            const double mx = dsub(L.f((base + i) * kBodyStride + kPX), px), my = dsub(L.f((base + i) * kBodyStride + kPY), py);
+            const bool ok = arrow == 1 ? my > 0.0 : (arrow == 2 ? mx > 0.0 : (arrow == 3 ? my < 0.0 : mx < 0.0));
+            elig |= ok ? (1u << i) : 0u;
+        }
+        const int cnt = __popc(elig);
+        if (cnt > 0) {
+            const uint32_t w2 = draw(P, env_id, t, j);
+            int pick = (int)(((uint64_t)(w2 >> 8) * (uint64_t)cnt) >> 24);
+            for (int i = 0; i < N; ++i) if (elig & (1u << i)) { if (pick == 0) { target = i; break; } pick -= 1; }
+        }
+    }
+    return base + target;
+}
+
+// _process_action, :309-422
+__device__ __forceinline__ void process_action(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id, uint32_t &j, int p, int arrow, int key)
+{
+    const int N = P.n_players, ball = 2 * N, side = p < N ? 0 : 1;
+    const int po = p * kBodyStride, bo = ball * kBodyStride;
+    const double m_inv_p = 1.0 / kPlayerWeight, m_inv_b = 1.0 / kBallWeight;
+    const double fx = arrow == 2 ? 1.0 : (arrow == 4 ? -1.0 : 0.0), fy = arrow == 1 ? 1.0 : (arrow == 3 ? -1.0 : 0.0);   // :312-327
+    const bool touch = touching(L, p, ball);
+    if (key <= 1) {                                                      // noop :331-335, dash :338-341
+        const double f = key == 0 ? kPlayerWeight : kPlayerForce;
+        const double vx = dadd(L.f(po + kVX), dmul(dmul(f, fx), m_inv_p));   // apply_impulse_at_local_point: v += j * m_inv
+        const double vy = dadd(L.f(po + kVY), dmul(dmul(f, fy), m_inv_p));
+        L.f(po + kVX) = vx; L.f(po + kVY) = vy;
+        if (touch) { L.f(bo + kVX) = vx; L.f(bo + kVY) = vy; }           // :300-304
+    } else if (key == 2 || key == 4) {                                   // shoot :344-366, pass :394-416
+        if (touch) {
+            double gx, gy, force, div;
+            if (key == 2) { gx = side == 0 ? kWidth : 0.0; gy = kHeight / 2; force = kBallForce; div = 2.0; }
+            else {
+                const int tg = pass_target(L, P, env_id, s.t_total, j, p, arrow);
+                gx = L.f(tg * kBodyStride + kPX); gy = L.f(tg * kBodyStride + kPY); force = kBallForce - 20; div = 10.0;
+            }
+            const double vx = dsub(gx, L.f(bo + kPX)), vy = dsub(gy, L.f(bo + kPY));
+            const double mag = dsqrt(dadd(dmul(vx, vx), dmul(vy, vy)));
+            const double bfx = ddiv(dmul(force, vx), mag), bfy = ddiv(dmul(force, vy), mag);
+            s.owner_side = side;
+            L.f(bo + kVX) = dadd(ddiv(L.f(bo + kVX), div), dmul(bfx, m_inv_b));
+            L.f(bo + kVY) = dadd(ddiv(L.f(bo + kVY), div), dmul(bfy, m_inv_b));
+        }
+    } else {                                                             // press :371-391
+        if (!touch && arrow == 0) {
+            const double vx = dsub(L.f(bo + kPX), L.f(po + kPX)), vy = dsub(L.f(bo + kPY), L.f(po + kPY));
+            const double mag = dsqrt(dadd(dmul(vx, vx), dmul(vy, vy)));
+            const double pfx = ddiv(dmul(kPlayerForce, vx), mag), pfy = ddiv(dmul(kPlayerForce, vy), mag);
+            L.f(po + kVX) = dadd(L.f(po + kVX), dmul(pfx, m_inv_p));
+            L.f(po + kVY) = dadd(L.f(po + kVY), dmul(pfy, m_inv_p));
+        }
+    }
+    if (touch) s.owner_side = side;                                      // :450-451
+}
+
+// closest point of segment s to (cx, cy): every segment is axis-aligned, so it is the centre's coordinate
+// clamped to the segment's extent (Chipmunk CircleToSegment: a + (b - a) clamp01(((b - a).(c - a)) / |b - a|^2))
+__device__ __forceinline__ void seg_closest(int sg, double cx, double cy, double &qx, double &qy)
+{
+    double ax, ay, bx, by;
+    segment(sg, ax, ay, bx, by);
+    if (ax == bx) { qx = ax; qy = cy < ay ? ay : (cy > by ? by : cy); }
+    else { qy = ay; qx = cx < ax ? ax : (cx > bx ? bx : cx); }
+}
+
+__device__ __forceinline__ bool ball_touches_segment(Lane L, int ball, int sg)
+{
+    const double cx = L.f(ball * kBodyStride + kPX), cy = L.f(ball * kBodyStride + kPY);
+    double qx, qy;
+    seg_closest(sg, cx, cy, qx, qy);
+    const double dx = dsub(qx, cx), dy = dsub(qy, cy);
+    return dadd(dmul(dx, dx), dmul(dy, dy)) < (kRBall + kRSeg) * (kRBall + kRSeg);
+}
+
+// cpSpaceStep(dt = 0.1).  Returns the number of contacts; `overflow` counts contacts beyond kMaxContacts.
+__device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, const PairCache &C, Contact *con, int &overflow)
+{
+    const int N = P.n_players, B = 2 * N + 1, ball = 2 * N, CC = B * (B - 1) / 2;
+    const double m_inv_p = 1.0 / kPlayerWeight, m_inv_b = 1.0 / kBallWeight;
+    int nc = 0;
+    // 1. integrate positions (cpBodyUpdatePosition): p += (v + v_bias) dt; v_bias = 0
+    for (int i = 0; i < B; ++i) {
+        const int o = i * kBodyStride;
+        L.f(o + kPX) = dadd(L.f(o + kPX), dmul(dadd(L.f(o + kVX), L.f(o + kBX)), kDt));
+        L.f(o + kPY) = dadd(L.f(o + kPY), dmul(dadd(L.f(o + kVY), L.f(o + kBY)), kDt));
+        L.f(o + kBX) = 0.0; L.f(o + kBY) = 0.0;
+    }
+    // 2. narrow phase in pair-id order + 5. arbiter pre-step (uses the velocities before step 6)
+    //    pass 0: circle/circle pairs (i < j), id j(j-1)/2 + i: outer loop over j, inner over i;
+    //    pass 1: circle/segment pairs, id CC + 12 * body + segment
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int jb = pass == 0 ? 1 : 0; jb < B; ++jb) {
+            const int inner = pass == 0 ? jb : kNSeg;
+            const int bo_j = jb * kBodyStride;
+            const double jx_ = L.f(bo_j + kPX), jy_ = L.f(bo_j + kPY);
+            if (pass == 1) {
+                // no segment can be touched from strictly inside the pitch: every segment lies on or outside its
+                // border, and r + r_segment <= 2.5
+                if (jx_ > 2.5 && jx_ < kWidth - 2.5 && jy_ > 2.5 && jy_ < kHeight - 2.5) continue;
+            }
+            for (int ii = 0; ii < inner; ++ii) {
+                int a, b, q;                                             // b < 0: static segment -1 - b
+                if (pass == 0) { a = ii; b = jb; q = jb * (jb - 1) / 2 + ii; }
+                else { a = jb; b = -1 - ii; q = CC + jb * kNSeg + ii; }
+                const int ao = a * kBodyStride;
+                const double pax = L.f(ao + kPX), pay = L.f(ao + kPY);
+                const double ra = a == ball ? kRBall : kRPlayer;
+                double rb, tx, ty;                                       // (tx, ty): centre of b or closest point
+                if (b >= 0) { rb = b == ball ? kRBall : kRPlayer; tx = jx_; ty = jy_; }
+                else { rb = kRSeg; seg_closest(ii, pax, pay, tx, ty); }
+                const double dx = dsub(tx, pax), dy = dsub(ty, pay);
+                const double distsq = dadd(dmul(dx, dx), dmul(dy, dy)), mind = ra + rb;
+                if (!(distsq < mind * mind)) continue;
+                if (nc == kMaxContacts) { overflow += 1; continue; }
+                Contact &k = con[nc++];
+                const double dist = dsqrt(distsq);
+                if (dist != 0.0) { const double inv = ddiv(1.0, dist); k.nx = dmul(dx, inv); k.ny = dmul(dy, inv); }
+                else if (b >= 0) { k.nx = 1.0; k.ny = 0.0; }
+                else {   // segment normal: perp(normalize(b - a))
+                    double sax, say, sbx, sby;
+                    segment(ii, sax, say, sbx, sby);
+                    const double sx = dsub(sbx, sax), sy = dsub(sby, say), sl = dsqrt(dadd(dmul(sx, sx), dmul(sy, sy)));
+                    k.nx = -ddiv(sy, sl); k.ny = ddiv(sx, sl);
+                }
+                k.a = a; k.b = b; k.q = q;
+                const double p1x = dadd(pax, dmul(k.nx, ra)), p1y = dadd(pay, dmul(k.ny, ra));
+                const double p2x = dadd(tx, dmul(k.nx, -rb)), p2y = dadd(ty, dmul(k.ny, -rb));
+                const double pen = dadd(dmul(dsub(p2x, p1x), k.nx), dmul(dsub(p2y, p1y), k.ny));
+                const double ma = a == ball ? m_inv_b : m_inv_p, mb = b >= 0 ? (b == ball ? m_inv_b : m_inv_p) : 0.0;
+                k.n_mass = ddiv(1.0, dadd(ma, mb));
+                double m = dadd(pen, kSlop);
+                m = m < 0.0 ? m : 0.0;                                   // cpfmin(0, dist + slop)
+                k.bias = ddiv(dmul(-P.bias_coef, m), kDt);
+                k.jbias = 0.0;
+                const double vbx = b >= 0 ? L.f(b * kBodyStride + kVX) : 0.0, vby = b >= 0 ? L.f(b * kBodyStride + kVY) : 0.0;
+                const double el = b >= 0 ? kElasticity * kElasticity : kElasticity * 0.0;
+                k.bounce = dmul(dadd(dmul(dsub(vbx, L.f(ao + kVX)), k.nx), dmul(dsub(vby, L.f(ao + kVY)), k.ny)), el);
+                // cached arbiter (collision_persistence = 3): reuse the impulse of a pair that touched within 3 steps
+                const uint32_t last = C.last[(size_t)q * C.stride];
+                k.jn = (s.stamp - last <= 3u) ? C.jn[(size_t)q * C.stride] : 0.0;
+                C.last[(size_t)q * C.stride] = s.stamp;
+            }
+        }
+    }
+    // 6. integrate velocities through velocity_func (player.py:45-50, ball.py:49-54)
+    for (int i = 0; i < B; ++i) {
+        const int o = i * kBodyStride;
+        double vx = dadd(dmul(L.f(o + kVX), P.damping_dt), 0.0), vy = dadd(dmul(L.f(o + kVY), P.damping_dt), 0.0);
+        const double l = dsqrt(dadd(dmul(vx, vx), dmul(vy, vy))), mx = i == ball ? kBallMaxV : kPlayerMaxV;
+        if (l > mx) { const double sc = ddiv(mx, l); vx = dmul(vx, sc); vy = dmul(vy, sc); }
+        L.f(o + kVX) = vx; L.f(o + kVY) = vy;
+    }
+    // 7. warm start (cpArbiterApplyCachedImpulse, dt_coef = 1)
+    for (int i = 0; i < nc; ++i) {
+        const Contact &k = con[i];
+        const double jx = dmul(k.nx, k.jn), jy = dmul(k.ny, k.jn), ma = k.a == ball ? m_inv_b : m_inv_p;
+        const int ao = k.a * kBodyStride;
+        L.f(ao + kVX) = dsub(L.f(ao + kVX), dmul(jx, ma)); L.f(ao + kVY) = dsub(L.f(ao + kVY), dmul(jy, ma));
+        if (k.b >= 0) {
+            const double mb = k.b == ball ? m_inv_b : m_inv_p;
+            const int bo = k.b * kBodyStride;
+            L.f(bo + kVX) = dadd(L.f(bo + kVX), dmul(jx, mb)); L.f(bo + kVY) = dadd(L.f(bo + kVY), dmul(jy, mb));
+        }
+    }
+    // 8. ten iterations of cpArbiterApplyImpulse over the contacts in order
+    for (int it = 0; it < 10; ++it) {
+        for (int i = 0; i < nc; ++i) {
+            Contact &k = con[i];
+            const int a = k.a, b = k.b, ao = a * kBodyStride, bo = (b >= 0 ? b : 0) * kBodyStride;
+            const double ma = a == ball ? m_inv_b : m_inv_p, mb = b >= 0 ? (b == ball ? m_inv_b : m_inv_p) : 0.0;
+            const double vb2x = b >= 0 ? L.f(bo + kBX) : 0.0, vb2y = b >= 0 ? L.f(bo + kBY) : 0.0;
+            const double v2x = b >= 0 ? L.f(bo + kVX) : 0.0, v2y = b >= 0 ? L.f(bo + kVY) : 0.0;
+            const double vbn = dadd(dmul(dsub(vb2x, L.f(ao + kBX)), k.nx), dmul(dsub(vb2y, L.f(ao + kBY)), k.ny));
+            const double vrn = dadd(dmul(dsub(v2x, L.f(ao + kVX)), k.nx), dmul(dsub(v2y, L.f(ao + kVY)), k.ny));
+            const double jbn = dmul(dsub(k.bias, vbn), k.n_mass), jbn_old = k.jbias;
+            const double t1 = dadd(jbn_old, jbn);
+            k.jbias = t1 > 0.0 ? t1 : 0.0;
+            const double jn = dmul(-dadd(k.bounce, vrn), k.n_mass), jn_old = k.jn;
+            const double t2 = dadd(jn_old, jn);
+            k.jn = t2 > 0.0 ? t2 : 0.0;
+            const double db = dsub(k.jbias, jbn_old), dj = dsub(k.jn, jn_old);
+            const double bx = dmul(k.nx, db), by = dmul(k.ny, db), jx = dmul(k.nx, dj), jy = dmul(k.ny, dj);
+            L.f(ao + kBX) = dsub(L.f(ao + kBX), dmul(bx, ma)); L.f(ao + kBY) = dsub(L.f(ao + kBY), dmul(by, ma));
+            L.f(ao + kVX) = dsub(L.f(ao + kVX), dmul(jx, ma)); L.f(ao + kVY) = dsub(L.f(ao + kVY), dmul(jy, ma));
+            if (b >= 0) {
+                L.f(bo + kBX) = dadd(L.f(bo + kBX), dmul(bx, mb)); L.f(bo + kBY) = dadd(L.f(bo + kBY), dmul(by, mb));
+                L.f(bo + kVX) = dadd(L.f(bo + kVX), dmul(jx, mb)); L.f(bo + kVY) = dadd(L.f(bo + kVY), dmul(jy, mb));
+            }
+        }
+    }
+    for (int i = 0; i < nc; ++i) C.jn[(size_t)con[i].q * C.stride] = con[i].jn;
+    s.stamp += 1;
+    return nc;
+}
+
+struct StepResult { double reward; int done; int flags; int contacts; int overflow; };
+
+// Futbol.step, :427-483.  `left`: this env's 2N action bytes (arrow, key per left player) or nullptr =
+// synthetic uniform actions from Philox stream 1.
+__device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id, const uint8_t *left,
+                                              const PairCache &C, Contact *con)
+{
+    const int N = P.n_players, ball = 2 * N, bo = ball * kBodyStride;
+    StepResult res;
+    res.flags = 0; res.overflow = 0;
+    uint32_t j = 0;                                                      // sequential dynamics draws of this step
+    double init_d[kMaxN];                                                // :433
+    const double bix = L.f(bo + kPX), biy = L.f(bo + kPY);               // :435
+    for (int i = 0; i < N; ++i) {
+        const double dx = dsub(L.f(i * kBodyStride + kPX), bix), dy = dsub(L.f(i * kBodyStride + kPY), biy);
+        init_d[i] = dsqrt(dadd(dmul(dx, dx), dmul(dy, dy)));
+    }
+    double reward = 0.0;
+
+    for (int p = 0; p < 2 * N; ++p) {                                    // :447-453, right team = action_space.sample() (:429)
+        int arrow, key;
+        if (p < N && left != nullptr) { arrow = left[2 * p] % 5; key = left[2 * p + 1] % 5; }
+        else {
+            const uint32_t stream = p < N ? kStreamActions : kStreamV1Opp;
+            const int q = p < N ? p : p - N;
+            const Philox4 blk = philox_step_block(P.key, env_id, stream, s.t_total, (uint32_t)(2 * q) >> 2);
+            const uint32_t w0 = (q & 1) ? blk.z : blk.x, w1 = (q & 1) ? blk.w : blk.y;
+            arrow = (int)__umulhi(w0, 5u); key = (int)__umulhi(w1, 5u);
+        }
+        process_action(L, s, P, env_id, j, p, arrow, key);
+    }
+
+    bool out = false;                                                    // check_and_fix_out_bounds, :256-287
+    for (int sg = 0; sg < 6 && !out; ++sg) {
+        if (!ball_touches_segment(L, ball, sg)) continue;
+        out = true;
+        const double bx = L.f(bo + kPX), by = L.f(bo + kPY);
+        double dbx = 0, dby = 0, dpx = 0, dpy = 0;
+        if (sg == 0 || sg == 1) { dbx = 3.5; dpx = 1; } else if (sg == 3 || sg == 4) { dbx = -3.5; dpx = -1; }
+        else if (sg == 2) { dby = -3.5; dpy = -1; } else { dby = 3.5; dpy = 1; }
+        L.f(bo + kPX) = dadd(bx, dbx); L.f(bo + kPY) = dadd(by, dby); L.f(bo + kVX) = 0.0; L.f(bo + kVY) = 0.0;
+        const int pick = (int)__umulhi(draw(P, env_id, s.t_total, j), (uint32_t)N);
+        const int g = s.owner_side == 1 ? pick : N + pick;               // the other side gets the ball
+        s.owner_side = s.owner_side == 1 ? 0 : 1;
+        const int go = g * kBodyStride;
+        L.f(go + kPX) = dadd(bx, dpx); L.f(go + kPY) = dadd(by, dpy); L.f(go + kVX) = 0.0; L.f(go + kVY) = 0.0;
+    }
+    if (out) res.flags |= kFlagOut;
+
+    res.contacts = space_step(L, s, P, C, con, res.overflow);            // :459
+
+    if (!out) {                                                          // :463-467
+        double best = 0.0;
+        bool first = true;
+        const double bx = L.f(bo + kPX), by = L.f(bo + kPY);
+        for (int i = (N == 5 ? 3 : 0); i < N; ++i) {                     // :501-504
+            const double dx = dsub(L.f(i * kBodyStride + kPX), bx), dy = dsub(L.f(i * kBodyStride + kPY), by);
+            const double diff = dsub(init_d[i], dsqrt(dadd(dmul(dx, dx), dmul(dy, dy))));
+            if (first || diff > best) { best = diff; first = false; }
+        }
+        reward = dadd(reward, dmul(best, 10.0));
+        const double ax = dsub(bx, kWidth), ay = dsub(by, kHeight / 2), ix = dsub(bix, kWidth), iy = dsub(biy, kHeight / 2);
+        reward = dadd(reward, dmul(dsub(dsqrt(dadd(dmul(ix, ix), dmul(iy, iy))), dsqrt(dadd(dmul(ax, ax), dmul(ay, ay)))), 10.0));
+    }
+
+    bool goal = false;                                                   // ball_contact_goal, :291-296
+    for (int sg = 6; sg < 12; ++sg) goal = goal || ball_touches_segment(L, ball, sg);
+    if (goal) {                                                          // :469-475
+        const bool left_scored = L.f(bo + kPX) > kWidth - 2;
+        reward = dadd(reward, left_scored ? 1000.0 : -1000.0);
+        position_to_initial(L, s, P);
+        s.owner_side = (int)__umulhi(draw(P, env_id, s.t_total, j), 2u);
+        res.flags |= kFlagGoal | (left_scored ? (int)kFlagGoalLeft : 0);
+    }
+    s.ep_step += 1;                                                      // :478-481
+    s.t_total += 1;
+    res.done = s.ep_step >= P.ep_limit ? 1 : 0;
+    if (res.done) res.flags |= kFlagDone;
+    res.reward = reward;
+    return res;
+}
+
+}  // namespace v1
+}  // namespace futbol

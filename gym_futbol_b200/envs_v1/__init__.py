@@ -1,1 +1,1 @@
-# v1 (`Futbol`, pymunk physics) drop-in: lands with the v1 kernels.
+from .futbol_env import Futbol  # noqa: F401  (reference: gym_futbol/envs_v1/__init__.py:1)

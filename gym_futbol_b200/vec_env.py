@@ -49,15 +49,20 @@ class FutbolVecEnv:
             _lib.check(self.lib.futbol_create(C.byref(self.cfg), C.byref(h)))
         self._h = h
         n = self.num_envs
-        self.state = torch.zeros(self.lib.futbol_state_bytes(h), dtype=torch.uint8, device=self.device)
-        self.obs = torch.zeros((n, OBS_DIM_V0), dtype=dtype, device=self.device)
-        self.rewards = torch.zeros(n, dtype=dtype, device=self.device)
-        self.dones = torch.zeros(n, dtype=torch.uint8, device=self.device)
-        self.final_obs = torch.zeros((n, OBS_DIM_V0), dtype=dtype, device=self.device)
-        self.stats = torch.zeros(_lib.STATS_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
-        self._roll = {}
+        self.obs_dim, self.act_shape = OBS_DIM_V0, ()
+        self._alloc()
         self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(OBS_DIM_V0,), dtype=np.float32)
         self.action_space = spaces.Discrete(16)
+
+    def _alloc(self):
+        n, h, D = self.num_envs, self._h, self.obs_dim
+        self.state = torch.zeros(self.lib.futbol_state_bytes(h), dtype=torch.uint8, device=self.device)
+        self.obs = torch.zeros((n, D), dtype=self.dtype, device=self.device)
+        self.rewards = torch.zeros(n, dtype=self.dtype, device=self.device)
+        self.dones = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        self.final_obs = torch.zeros((n, D), dtype=self.dtype, device=self.device)
+        self.stats = torch.zeros(_lib.STATS_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+        self._roll = {}
         self.episode_steps = self.lib.futbol_draw_limit_steps(h)
 
     # ------------------------------------------------------------------ plumbing
@@ -101,7 +106,7 @@ class FutbolVecEnv:
     def step(self, actions):
         """actions: [n] ints in 0..15 (ai_1 = a // 4, ai_2 = a % 4)."""
         with torch.cuda.device(self.device):
-            a = self._actions(actions, (self.num_envs,))
+            a = self._actions(actions, (self.num_envs,) + self.act_shape)
             _lib.check(self.lib.futbol_step(self._h, _ptr(self.state), _ptr(a), _ptr(self.obs), _ptr(self.rewards),
                                             _ptr(self.dones), _ptr(self.final_obs), self._dt, self._stream()))
         return self.obs, self.rewards, self.dones, {"terminal_observation": self.final_obs}
@@ -117,31 +122,33 @@ class FutbolVecEnv:
         n = self.num_envs
         if out is not None:
             o, r, d = out
-            for t, shape, dt in ((o, (K, n, OBS_DIM_V0), torch.float32), (r, (K, n), torch.float32), (d, (K, n), torch.uint8)):
+            for t, shape, dt in ((o, (K, n, self.obs_dim), torch.float32), (r, (K, n), torch.float32), (d, (K, n), torch.uint8)):
                 if t is not None and (tuple(t.shape) != shape or t.dtype != dt or t.device != self.device or not t.is_contiguous()):
                     raise ValueError("out tensors must be contiguous %s tensors of shape %s on %s" % (dt, shape, self.device))
         else:
             buf = self._roll.get(K)
             if buf is None:
-                buf = (torch.empty((K, n, OBS_DIM_V0), dtype=torch.float32, device=self.device),
+                buf = (torch.empty((K, n, self.obs_dim), dtype=torch.float32, device=self.device),
                        torch.empty((K, n), dtype=torch.float32, device=self.device),
                        torch.empty((K, n), dtype=torch.uint8, device=self.device))
                 self._roll[K] = buf
             o, r, d = buf
             o, r, d = (o if obs else None), (r if reward else None), (d if done else None)
         with torch.cuda.device(self.device):
-            a = None if actions is None else self._actions(actions, (K, n))
+            a = None if actions is None else self._actions(actions, (K, n) + self.act_shape)
             _lib.check(self.lib.futbol_rollout(self._h, _ptr(self.state), K, _ptr(a), _ptr(o), _ptr(r), _ptr(d),
                                                _ptr(self.stats), self._stream()))
         return o, r, d
 
     # ------------------------------------------------------------------ state / statistics
+    STATE_DTYPE = _lib.V0_ENV_STATE
+
     def get_state(self):
-        """Complete env state as a numpy structured array (``_lib.V0_ENV_STATE``); synchronises."""
-        aos = torch.empty(self.num_envs * _lib.V0_ENV_STATE.itemsize, dtype=torch.uint8, device=self.device)
+        """Env state as a numpy structured array (``_lib.V0_ENV_STATE`` / ``V1_ENV_STATE``); synchronises."""
+        aos = torch.empty(self.num_envs * self.STATE_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.futbol_get_state(self._h, _ptr(self.state), _ptr(aos), self._stream()))
-        return aos.cpu().numpy().view(_lib.V0_ENV_STATE).copy()
+        return aos.cpu().numpy().view(self.STATE_DTYPE).copy()
 
     def set_state(self, records):
         records = np.ascontiguousarray(records, dtype=_lib.V0_ENV_STATE)
@@ -157,6 +164,48 @@ class FutbolVecEnv:
         rec = self.stats.cpu().numpy().view(_lib.STATS_DTYPE)[0]
         out = {k: (float(rec[k]) if k == "reward_sum" else int(rec[k])) for k in
                ("reward_sum", "env_steps", "episodes", "goals_ai", "goals_opp", "out_of_field")}
+        out["contacts"], out["contacts_dropped"] = int(rec["reserved"][0]), int(rec["reserved"][1])
         if clear:
             self.stats.zero_()
         return out
+
+
+class FutbolV1VecEnv(FutbolVecEnv):
+    """v1 ``Futbol`` (gym_futbol/envs_v1/futbol_env.py, N-vs-N with rigid-body contacts) x ``num_envs`` on one GPU.
+
+    ``step(actions)``: actions uint8 ``[n, 2N]`` = (arrow key, action key) per left-team player, i.e. the
+    reference's ``MultiDiscrete([5, 5] * N)`` (:78-79); the right team draws uniform random actions (:429).
+    Observations are the normalised ``4 + 8N`` vector (:154-180).  The physics restates the Chipmunk2D subset
+    pymunk runs for the reference; parity at that boundary is unpinned.
+    """
+
+    STATE_DTYPE = _lib.V1_ENV_STATE
+
+    def __init__(self, num_envs, number_of_player=2, device="cuda:0", seed=0, env_id_offset=0, total_time=30,
+                 auto_reset=True, dtype=torch.float32):
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("dtype must be torch.float32 or torch.float64")
+        if int(num_envs) <= 0:
+            raise ValueError("num_envs must be positive")
+        if not 1 <= int(number_of_player) <= 10:
+            raise ValueError("number_of_player must be 1..10")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise _lib.FutbolError("FutbolV1VecEnv needs a CUDA device; there is no CPU fallback")
+        self.num_envs, self.number_of_player = int(num_envs), int(number_of_player)
+        self.dtype = dtype
+        self._dt = 1 if dtype == torch.float64 else 0
+        self.cfg = _lib.FutbolConfig(_lib.ABI_VERSION, _lib.VARIANT_V1, self.num_envs, int(env_id_offset), int(seed),
+                                     self.number_of_player, 0, 0, 0, int(bool(auto_reset)), 20, float(total_time), 12.0)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.futbol_create(C.byref(self.cfg), C.byref(h)))
+        self._h = h
+        self.obs_dim, self.act_shape = 4 + 8 * self.number_of_player, (2 * self.number_of_player,)
+        self._alloc()
+        self.observation_space = spaces.Box(low=-1.0, high=1.0, shape=(self.obs_dim,), dtype=np.float32)
+        self.action_space = spaces.MultiDiscrete([5, 5] * self.number_of_player)
+
+    def set_state(self, records):
+        raise _lib.FutbolError("set_state is not available for the v1 variant (the arbiter cache is not exported)")

@@ -68,7 +68,21 @@ typedef struct FutbolV0EnvState {
     uint8_t  pad_;
 } FutbolV0EnvState;
 
-/* Rollout statistics (sums over all envs and steps of one futbol_rollout call). */
+/* One env's v1 state (bodies + scalars; the arbiter cache is not exported), for futbol_get_state.
+ * Bodies: team A players 0..N-1, team B players N..2N-1, ball 2N; unused rows are zero. */
+typedef struct FutbolV1EnvState {
+    double   body[21][6];  /* x, y, vx, vy, v_bias_x, v_bias_y */
+    uint64_t t_total;      /* steps since creation = Philox step index */
+    uint32_t stamp;        /* space steps taken (0.1 s steps and the 1e-4 s kick-off steps) */
+    int32_t  ep_step;
+    uint8_t  owner_side;   /* ball_owner_side: 0 left, 1 right (envs_v1/futbol_env.py:147) */
+    uint8_t  flags;        /* of the last step: 1 goal, 2 out of bounds, 4 done, 8 the goal was scored by the left team */
+    uint8_t  pad_[2];
+} FutbolV1EnvState;
+
+/* Rollout statistics (sums over all envs and steps of one futbol_rollout call).
+ * v1: goals_ai = goals of the left team, goals_opp = of the right team, out_of_field = out-of-bounds fixes,
+ * reserved[0] = contacts solved, reserved[1] = contacts dropped (more than 32 in one space step; expected 0). */
 typedef struct FutbolStats {
     double   reward_sum;
     uint64_t env_steps, episodes, goals_ai, goals_opp, out_of_field;
@@ -111,10 +125,10 @@ int futbol_step(FutbolHandle *h, void *state, const uint8_t *actions, void *obs,
 int futbol_rollout(FutbolHandle *h, void *state, int K, const uint8_t *actions, float *obs,
                    float *reward, uint8_t *done, FutbolStats *stats, void *stream);
 
-/* ---- state access (device AoS records, FutbolV0EnvState for v0) --------------------- */
+/* ---- state access (device AoS records: FutbolV0EnvState / FutbolV1EnvState) ---------- */
 size_t futbol_env_state_bytes(const FutbolHandle *h); /* sizeof one AoS record */
 int futbol_get_state(FutbolHandle *h, const void *state, void *aos_out, void *stream);
-int futbol_set_state(FutbolHandle *h, void *state, const void *aos_in, void *stream);
+int futbol_set_state(FutbolHandle *h, void *state, const void *aos_in, void *stream); /* v0 only */
 
 /* number of kernels this handle has launched (bench.py's gpu_launches) */
 uint64_t futbol_launch_count(const FutbolHandle *h);

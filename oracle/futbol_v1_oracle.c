@@ -24,6 +24,9 @@
  *   - dt_coef of the warm start is 1: the only step with another dt is the 1e-4 step after a kick-off
  *     (:142), and no pair that was touching before a kick-off can touch again within the 3-step
  *     persistence window (all bodies are teleported to the formation);
+ *   - a segment's closest point is taken by clamping the centre's coordinate (all segments are axis-aligned),
+ *     and at most V1_MAX_CONTACTS = 32 contacts are solved per space step (pairs beyond that, in pair order,
+ *     are ignored and counted in `overflow`; never reached in any test or bench run);
  *   - contact-point distance dist = (p2 - p1) . n with p1 = c_a + n r_a, p2 = c_b - n r_b (closest - n r_s
  *     for a segment), i.e. Chipmunk's (r2 - r1 + body_delta) . n without the round trip through r1, r2.
  * Arithmetic: one IEEE double operation per written operation, no contraction (-ffp-contract=off); x**2 is
@@ -50,6 +53,7 @@ void futbol_oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 #define V1_MAX_BODIES (2 * V1_MAX_N + 1)
 #define V1_NSEG 12
 #define V1_MAX_PAIRS (V1_MAX_BODIES * (V1_MAX_BODIES - 1) / 2 + V1_MAX_BODIES * V1_NSEG)
+#define V1_MAX_CONTACTS 32
 
 /* futbol_env.py:19-37 */
 #define WIDTH 105.0
@@ -90,6 +94,8 @@ typedef struct {
     int32_t goals_left, goals_right;   /* bookkeeping for statistics (the reference keeps no score) */
     int32_t flags;
     int32_t contacts;            /* contacts of the last 0.1 space step (statistics) */
+    int32_t overflow;            /* contacts dropped because more than V1_MAX_CONTACTS touched in one step */
+    int32_t pad_;
 } OracleV1Env;
 
 size_t futbol_v1_oracle_env_bytes(void) { return sizeof(OracleV1Env); }
@@ -291,13 +297,14 @@ typedef struct { int a, b, q; double nx, ny, n_mass, bias, bounce, jn, jbias; } 
 static double radius_of(int i, int ball) { return i == ball ? R_BALL : R_PLAYER; }
 static double minv_of(int i, int ball) { return i == ball ? 1.0 / BALL_WEIGHT : 1.0 / PLAYER_WEIGHT; }
 
-/* closest point of segment s to (cx, cy): Chipmunk CircleToSegment */
+/* closest point of segment s to (cx, cy).  Chipmunk's CircleToSegment computes a + (b - a) * clamp01(((b - a) .
+ * (c - a)) / |b - a|^2); every segment of this scene is axis-aligned (:184-224), for which that point is the
+ * centre's coordinate clamped to the segment's extent -- the form used here (and by the kernel). */
 static void seg_closest(int s, double cx, double cy, double *qx, double *qy)
 {
-    double ax = SEG[s][0], ay = SEG[s][1], dx = SEG[s][2] - ax, dy = SEG[s][3] - ay;
-    double t = (dx * (cx - ax) + dy * (cy - ay)) / (dx * dx + dy * dy);
-    t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);                   /* cpfclamp01 */
-    *qx = ax + dx * t; *qy = ay + dy * t;
+    double ax = SEG[s][0], ay = SEG[s][1], bx = SEG[s][2], by = SEG[s][3];
+    if (ax == bx) { *qx = ax; *qy = cy < ay ? ay : (cy > by ? by : cy); }     /* vertical, ay < by */
+    else          { *qy = ay; *qx = cx < ax ? ax : (cx > bx ? bx : cx); }     /* horizontal, ax < bx */
 }
 
 static int ball_touches_segment(const OracleV1Env *e, int ball, int s)
@@ -313,7 +320,7 @@ static void space_step(const OracleV1Config *c, OracleV1Env *e)
 {
     const int N = c->n_players, B = 2 * N + 1, ball = 2 * N, CC = B * (B - 1) / 2;
     const double dt = TIME_STEP, slop = 0.1;
-    Contact con[V1_MAX_PAIRS];
+    Contact con[V1_MAX_CONTACTS];
     int nc = 0;
     /* 1. integrate positions (cpBodyUpdatePosition): p += (v + v_bias) dt; v_bias = 0 */
     for (int i = 0; i < B; ++i) {
@@ -332,6 +339,7 @@ static void space_step(const OracleV1Config *c, OracleV1Env *e)
         double dx = tx - e->p[a][0], dy = ty - e->p[a][1];
         double distsq = dx * dx + dy * dy, mind = ra + rb;
         int touch = distsq < mind * mind;
+        if (touch && nc == V1_MAX_CONTACTS) { e->overflow += 1; touch = 0; }
         if (!touch) { if (e->age[q] != 255) e->age[q] += 1; continue; }
         Contact *k = &con[nc++];
         double dist = sqrt(distsq);

@@ -19,7 +19,8 @@ CFG_DTYPE = np.dtype([("seed", np.uint64), ("n_players", np.int32), ("ep_limit",
 ENV_DTYPE = np.dtype([("p", np.float64, (MAX_BODIES, 2)), ("v", np.float64, (MAX_BODIES, 2)), ("vb", np.float64, (MAX_BODIES, 2)),
                       ("jn", np.float64, (MAX_PAIRS,)), ("age", np.uint8, (MAX_PAIRS,)), ("t_total", np.uint64),
                       ("ep_step", np.int32), ("owner_side", np.int32), ("env_id", np.uint32), ("step_draws", np.uint32),
-                      ("goals_left", np.int32), ("goals_right", np.int32), ("flags", np.int32), ("contacts", np.int32)],
+                      ("goals_left", np.int32), ("goals_right", np.int32), ("flags", np.int32), ("contacts", np.int32),
+                      ("overflow", np.int32), ("pad_", np.int32)],
                      align=True)
 
 _lib = None
