@@ -91,6 +91,8 @@ __device__ __forceinline__ void warp_store_obs_f32(Lane L, int N, float *stage, 
 template <typename T>
 __global__ void v1_reset_kernel(V1Params P, StateView v, const uint8_t *mask, T *obs, int init)
 {
+    const uint32_t form_base = stage_formation(P, blockDim.x >> 5, threadIdx.x, blockDim.x);
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_envs) return;
     if (mask != nullptr && mask[i] == 0) return;
@@ -98,8 +100,8 @@ __global__ void v1_reset_kernel(V1Params P, StateView v, const uint8_t *mask, T 
     const Lane L = make_lane(threadIdx.x >> 5, threadIdx.x & 31, N);
     const uint32_t env_id = P.env_id_offset + (uint32_t)i;
     V1Regs s;
-    if (init) init_env(L, s, P, env_id);
-    else { load_state(v, i, L, s, B); reset_env(L, s, P, env_id); }
+    if (init) init_env(L, s, P, env_id, form_base);
+    else { load_state(v, i, L, s, B); reset_env(L, s, P, env_id, form_base); }
     store_state(v, i, L, s, B, 0);
     if (obs != nullptr) thread_store_obs(obs + (size_t)i * obs_dim(N), L, N);
 }
@@ -107,6 +109,8 @@ __global__ void v1_reset_kernel(V1Params P, StateView v, const uint8_t *mask, T 
 template <typename T>
 __global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, T *obs, T *reward, uint8_t *done, T *final_obs)
 {
+    const uint32_t form_base = stage_formation(P, blockDim.x >> 5, threadIdx.x, blockDim.x);
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_envs) return;
     const int N = P.n_players, B = 2 * N + 1, D = obs_dim(N);
@@ -116,10 +120,10 @@ __global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, 
     Contact con[kMaxContacts];
     V1Regs s;
     load_state(v, i, L, s, B);
-    const StepResult r = v1_step(L, s, P, env_id, actions + (size_t)i * 2 * N, C, con);
+    const StepResult r = v1_step(L, s, P, env_id, actions + (size_t)i * 2 * N, C, con, form_base);
     if (r.done && P.auto_reset) {
         if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * D, L, N);
-        reset_env(L, s, P, env_id);
+        reset_env(L, s, P, env_id, form_base);
     }
     store_state(v, i, L, s, B, r.flags);
     if (obs != nullptr) thread_store_obs(obs + (size_t)i * D, L, N);
@@ -130,6 +134,8 @@ __global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, 
 __global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t *__restrict__ actions, float *__restrict__ obs,
                                   float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
 {
+    const uint32_t form_base = stage_formation(P, blockDim.x >> 5, threadIdx.x, blockDim.x);
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warp_env0 = i - lane;
@@ -149,7 +155,7 @@ __global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t 
 
     V1Regs s;
     if (live) load_state(v, i, L, s, B);
-    else init_env(L, s, P, env_id);
+    else init_env(L, s, P, env_id, form_base);
 
     double reward_sum = 0.0;
     uint32_t episodes = 0, goals_l = 0, goals_r = 0, outs = 0, contacts = 0, overflow = 0;
@@ -159,8 +165,8 @@ __global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t 
         const size_t slot = (size_t)k * n + (size_t)i;
         StepResult r;
         if (live) {
-            r = v1_step(L, s, P, env_id, actions != nullptr ? actions + slot * 2 * N : nullptr, C, con);
-            if (r.done && P.auto_reset) reset_env(L, s, P, env_id);
+            r = v1_step(L, s, P, env_id, actions != nullptr ? actions + slot * 2 * N : nullptr, C, con, form_base);
+            if (r.done && P.auto_reset) reset_env(L, s, P, env_id, form_base);
         } else {
             r.reward = 0.0; r.done = 0; r.flags = 0; r.contacts = 0; r.overflow = 0;
         }
@@ -218,7 +224,7 @@ __global__ void v1_get_state_kernel(int n, int n_players, StateView v, FutbolV1E
 // ---- host launchers ------------------------------------------------------------------------------------
 static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 static inline int threads_for(int n_players) { return n_players <= 5 ? 64 : 32; }   // keeps a block under 48 KB of shared memory
-static inline int smem_for(int n_players) { return (threads_for(n_players) / 32) * warp_smem_bytes(n_players); }
+static inline int smem_for(int n_players) { return block_smem_bytes(n_players, threads_for(n_players) / 32); }
 
 cudaError_t launch_reset(const V1Params &P, void *state, const uint8_t *mask, void *obs, int obs_f64, int init, cudaStream_t st)
 {

@@ -34,24 +34,27 @@ enum : int { kFlagGoal = 1, kFlagOut = 2, kFlagDone = 4, kFlagGoalLeft = 8 };
 constexpr uint32_t kResetBlock = 0x4000u;   // Philox block of the side drawn by reset()
 constexpr uint32_t kStamp0 = 8;             // first space-step stamp (cache entries start at 0 = "never touched")
 
-// the 12 segments of _setup_walls (:184-224): six boundary segments, then six goal-box segments
+// the 12 segments of _setup_walls (:184-224): six boundary segments, then six goal-box segments; (ax, ay, bx, by)
+#ifndef FUTBOL_HOST_SHIM
+__constant__
+#endif
+static const double kSegments[kNSeg][4] = {
+    {0, 0, 0, kHeight / 2 - kGoalSize / 2},
+    {0, kHeight / 2 + kGoalSize / 2, 0, kHeight},
+    {0, kHeight, kWidth, kHeight},
+    {kWidth, 0, kWidth, kHeight / 2 - kGoalSize / 2},
+    {kWidth, kHeight / 2 + kGoalSize / 2, kWidth, kHeight},
+    {0, 0, kWidth, 0},
+    {-2, kHeight / 2 - kGoalSize / 2, -2, kHeight / 2 + kGoalSize / 2},
+    {-2, kHeight / 2 - kGoalSize / 2, 0, kHeight / 2 - kGoalSize / 2},
+    {-2, kHeight / 2 + kGoalSize / 2, 0, kHeight / 2 + kGoalSize / 2},
+    {kWidth + 2, kHeight / 2 - kGoalSize / 2, kWidth + 2, kHeight / 2 + kGoalSize / 2},
+    {kWidth, kHeight / 2 - kGoalSize / 2, kWidth + 2, kHeight / 2 - kGoalSize / 2},
+    {kWidth, kHeight / 2 + kGoalSize / 2, kWidth + 2, kHeight / 2 + kGoalSize / 2},
+};
 __device__ __forceinline__ void segment(int s, double &ax, double &ay, double &bx, double &by)
 {
-    const double lo = kHeight / 2 - kGoalSize / 2, hi = kHeight / 2 + kGoalSize / 2;
-    switch (s) {
-    case 0: ax = 0; ay = 0; bx = 0; by = lo; break;
-    case 1: ax = 0; ay = hi; bx = 0; by = kHeight; break;
-    case 2: ax = 0; ay = kHeight; bx = kWidth; by = kHeight; break;
-    case 3: ax = kWidth; ay = 0; bx = kWidth; by = lo; break;
-    case 4: ax = kWidth; ay = hi; bx = kWidth; by = kHeight; break;
-    case 5: ax = 0; ay = 0; bx = kWidth; by = 0; break;
-    case 6: ax = -2; ay = lo; bx = -2; by = hi; break;
-    case 7: ax = -2; ay = lo; bx = 0; by = lo; break;
-    case 8: ax = -2; ay = hi; bx = 0; by = hi; break;
-    case 9: ax = kWidth + 2; ay = lo; bx = kWidth + 2; by = hi; break;
-    case 10: ax = kWidth; ay = lo; bx = kWidth + 2; by = lo; break;
-    default: ax = kWidth; ay = hi; bx = kWidth + 2; by = hi; break;
-    }
+    ax = kSegments[s][0]; ay = kSegments[s][1]; bx = kSegments[s][2]; by = kSegments[s][3];
 }
 
 struct V1Params {
@@ -73,7 +76,7 @@ struct V1Params {
 #ifndef FUTBOL_HOST_SHIM
 extern __shared__ __align__(16) unsigned char futbol_smem[];
 #else
-static unsigned char futbol_smem[8 * 6 * kMaxBodies + 4 * (4 + 8 * kMaxN)] __attribute__((aligned(16)));
+static unsigned char futbol_smem[8 * 6 * kMaxBodies + 4 * (4 + 8 * kMaxN) + 8 * 4 * kMaxN] __attribute__((aligned(16)));
 #endif
 constexpr int kPX = 0, kPY = kLanes, kVX = 2 * kLanes, kVY = 3 * kLanes, kBX = 4 * kLanes, kBY = 5 * kLanes;
 constexpr int kBodyStride = 6 * kLanes;
@@ -86,6 +89,7 @@ struct Lane {
 __host__ __device__ constexpr int warp_state_bytes(int n_players) { return 6 * (2 * n_players + 1) * kLanes * 8; }
 __host__ __device__ constexpr int obs_dim(int n_players) { return 4 + 8 * n_players; }
 __host__ __device__ constexpr int warp_smem_bytes(int n_players) { return warp_state_bytes(n_players) + obs_dim(n_players) * kLanes * 4; }
+__host__ __device__ constexpr int block_smem_bytes(int n_players, int warps) { return warps * warp_smem_bytes(n_players) + 4 * n_players * 8; }
 __host__ __device__ constexpr int n_pairs(int bodies) { return bodies * (bodies - 1) / 2 + bodies * kNSeg; }
 
 __device__ __forceinline__ Lane make_lane(int warp_in_block, int lane, int n_players)
@@ -112,52 +116,79 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
-
-__device__ __forceinline__ uint32_t philox_word(const V1Params &P, uint32_t env_id, uint32_t stream, uint64_t t, uint32_t j)
+// c ? a : b that the optimiser cannot look through: keeps a zero operand off the slow path of the IEEE sqrt
+// sequence (see v0_step.cuh `pick`)
+#ifndef FUTBOL_HOST_SHIM
+__device__ __forceinline__ double pick(bool c, double a, double b)
 {
-    const Philox4 p = philox_step_block(P.key, env_id, stream, t, j >> 2);
-    const uint32_t lo = (j & 1u) ? p.y : p.x, hi = (j & 1u) ? p.w : p.z;
-    return (j & 2u) ? hi : lo;
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b), "r"((int)c));
+    return r;
 }
-// sequential dynamics draw (stream 3): rare (pass target, out-of-bounds receiver, side after a goal)
+#else
+inline double pick(bool c, double a, double b) { return c ? a : b; }
+#endif
+
+// One Philox word for the rare draws (pass target, out-of-bounds receiver, side after a goal / reset): out of line
+// and keyed by the seed (the round keys are re-derived) so that the hot loop carries a single inlined Philox.
+static __device__ __noinline__ uint32_t philox_word_cold(uint64_t seed, uint32_t env_id, uint32_t stream, uint64_t t, uint32_t block, uint32_t w)
+{
+    const PhiloxKey K = philox_expand_key(seed);
+    const Philox4 p = philox_step_block(K, env_id, stream, t, block);
+    const uint32_t lo = (w & 1u) ? p.y : p.x, hi = (w & 1u) ? p.w : p.z;
+    return (w & 2u) ? hi : lo;
+}
+// sequential dynamics draw (stream 3)
 __device__ __forceinline__ uint32_t draw(const V1Params &P, uint32_t env_id, uint64_t t, uint32_t &j)
 {
-    const uint32_t w = philox_word(P, env_id, kStreamV1Dynamics, t, j);
+    const uint32_t w = philox_word_cold(P.seed, env_id, kStreamV1Dynamics, t, j >> 2, j & 3u);
     j += 1;
     return w;
 }
 
 // _position_to_initial, :129-143: teleport to the formation, zero velocities, space.step(1e-4).  With all
 // velocities zero the 1e-4 step only consumes the bias velocities (p += v_bias * 1e-4, v_bias = 0), finds no
-// contact (formation spacing >= 13.6) and ages the cached arbiters by one step.
-__device__ __forceinline__ void position_to_initial(Lane L, V1Regs &s, const V1Params &P)
+// contact (formation spacing >= 13.6) and ages the cached arbiters by one step.  Out of line (three call sites);
+// the formation is read from the block's copy in shared memory (form_base: index in doubles, x then y).
+static __device__ __noinline__ void position_to_initial(Lane L, int N, uint32_t form_base)
 {
-    const int N = P.n_players, B = 2 * N + 1;
+    const int B = 2 * N + 1;
+    const double *form = reinterpret_cast<const double *>(futbol_smem) + form_base;
+#pragma unroll 1
     for (int i = 0; i < B; ++i) {
         const int o = i * kBodyStride;
-        const double x = i < 2 * N ? P.form_x[i] : dmul(kWidth, 0.5), y = i < 2 * N ? P.form_y[i] : dmul(kHeight, 0.5);
+        const double x = i < 2 * N ? form[i] : dmul(kWidth, 0.5), y = i < 2 * N ? form[2 * N + i] : dmul(kHeight, 0.5);
         L.f(o + kPX) = dadd(x, dmul(dadd(0.0, L.f(o + kBX)), 0.0001));
         L.f(o + kPY) = dadd(y, dmul(dadd(0.0, L.f(o + kBY)), 0.0001));
         L.f(o + kVX) = 0.0; L.f(o + kVY) = 0.0; L.f(o + kBX) = 0.0; L.f(o + kBY) = 0.0;
     }
+}
+
+// every kernel copies the formation of its launch parameters to the tail of the block's shared memory once
+__device__ __forceinline__ uint32_t stage_formation(const V1Params &P, int warps_in_block, int tid, int nthreads)
+{
+    const uint32_t base = (uint32_t)(warps_in_block * (warp_smem_bytes(P.n_players) / 8));
+    double *form = reinterpret_cast<double *>(futbol_smem) + base;
+    for (int i = tid; i < 2 * P.n_players; i += nthreads) { form[i] = P.form_x[i]; form[2 * P.n_players + i] = P.form_y[i]; }
+    return base;
+}
+
+__device__ __forceinline__ void reset_env(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id, uint32_t form_base)
+{   // Futbol.reset, :145-150 (t_total, the Philox step index, is deliberately kept; so is the arbiter cache)
+    s.ep_step = 0;
+    s.owner_side = (int)__umulhi(philox_word_cold(P.seed, env_id, kStreamV1Dynamics, s.t_total, kResetBlock, 0u), 2u);
+    position_to_initial(L, P.n_players, form_base);
     s.stamp += 1;
 }
 
-__device__ __forceinline__ void reset_env(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id)
-{   // Futbol.reset, :145-150 (t_total, the Philox step index, is deliberately kept; so is the arbiter cache)
-    s.ep_step = 0;
-    s.owner_side = (int)__umulhi(philox_step_block(P.key, env_id, kStreamV1Dynamics, s.t_total, kResetBlock).x, 2u);
-    position_to_initial(L, s, P);
-}
-
 // first construction (Futbol.__init__ -> reset): zero bias velocities, fresh stamps
-__device__ __forceinline__ void init_env(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id)
+__device__ __forceinline__ void init_env(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id, uint32_t form_base)
 {
     const int B = 2 * P.n_players + 1;
     for (int i = 0; i < B; ++i) { L.f(i * kBodyStride + kBX) = 0.0; L.f(i * kBodyStride + kBY) = 0.0; }
     s.t_total = 0;
     s.stamp = kStamp0;
-    reset_env(L, s, P, env_id);
+    reset_env(L, s, P, env_id, form_base);
 }
 
 // observation element k of the normalised vector [ball, team A, team B], :154-180
@@ -203,45 +234,45 @@ __device__ __forceinline__ int pass_target(Lane L, const V1Params &P, uint32_t e
     return base + target;
 }
 
-// _process_action, :309-422
+// _process_action, :309-422.  The common keys (noop, dash, press) are one straight-line block with selects; only
+// a kick (shoot / pass while touching the ball: a few percent of the turns) stays behind a branch.
 __device__ __forceinline__ void process_action(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id, uint32_t &j, int p, int arrow, int key)
 {
     const int N = P.n_players, ball = 2 * N, side = p < N ? 0 : 1;
     const int po = p * kBodyStride, bo = ball * kBodyStride;
     const double m_inv_p = 1.0 / kPlayerWeight, m_inv_b = 1.0 / kBallWeight;
     const double fx = arrow == 2 ? 1.0 : (arrow == 4 ? -1.0 : 0.0), fy = arrow == 1 ? 1.0 : (arrow == 3 ? -1.0 : 0.0);   // :312-327
-    const bool touch = touching(L, p, ball);
-    if (key <= 1) {                                                      // noop :331-335, dash :338-341
-        const double f = key == 0 ? kPlayerWeight : kPlayerForce;
-        const double vx = dadd(L.f(po + kVX), dmul(dmul(f, fx), m_inv_p));   // apply_impulse_at_local_point: v += j * m_inv
-        const double vy = dadd(L.f(po + kVY), dmul(dmul(f, fy), m_inv_p));
-        L.f(po + kVX) = vx; L.f(po + kVY) = vy;
-        if (touch) { L.f(bo + kVX) = vx; L.f(bo + kVY) = vy; }           // :300-304
-    } else if (key == 2 || key == 4) {                                   // shoot :344-366, pass :394-416
-        if (touch) {
-            double gx, gy, force, div;
-            if (key == 2) { gx = side == 0 ? kWidth : 0.0; gy = kHeight / 2; force = kBallForce; div = 2.0; }
-            else {
-                const int tg = pass_target(L, P, env_id, s.t_total, j, p, arrow);
-                gx = L.f(tg * kBodyStride + kPX); gy = L.f(tg * kBodyStride + kPY); force = kBallForce - 20; div = 10.0;
-            }
-            const double vx = dsub(gx, L.f(bo + kPX)), vy = dsub(gy, L.f(bo + kPY));
-            const double mag = dsqrt(dadd(dmul(vx, vx), dmul(vy, vy)));
-            const double bfx = ddiv(dmul(force, vx), mag), bfy = ddiv(dmul(force, vy), mag);
-            s.owner_side = side;
-            L.f(bo + kVX) = dadd(ddiv(L.f(bo + kVX), div), dmul(bfx, m_inv_b));
-            L.f(bo + kVY) = dadd(ddiv(L.f(bo + kVY), div), dmul(bfy, m_inv_b));
+    const double px = L.f(po + kPX), py = L.f(po + kPY), pvx = L.f(po + kVX), pvy = L.f(po + kVY);
+    const double dx = dsub(L.f(bo + kPX), px), dy = dsub(L.f(bo + kPY), py);          // player -> ball
+    const double d2 = dadd(dmul(dx, dx), dmul(dy, dy));
+    // Ball.has_contact_with, ball.py:39-40 = Chipmunk CircleToCircle: |delta|^2 < (r1 + r2)^2 (delta = p - ball there:
+    // the same squares)
+    const bool touch = d2 < (kRBall + kRPlayer) * (kRBall + kRPlayer);
+    const bool is_move = key <= 1;                                       // noop :331-335, dash :338-341
+    const bool is_press = key == 3 && !touch && arrow == 0;              // press :371-391 (not touching: d2 >= 6.25 > 0)
+    const double f = key == 0 ? kPlayerWeight : kPlayerForce;
+    const double mag = dsqrt(pick(is_press, d2, 1.0));
+    const double pfx = ddiv(dmul(kPlayerForce, pick(is_press, dx, 1.0)), mag), pfy = ddiv(dmul(kPlayerForce, pick(is_press, dy, 1.0)), mag);
+    // apply_impulse_at_local_point: v += j * m_inv
+    const double ivx = is_move ? dmul(dmul(f, fx), m_inv_p) : dmul(pfx, m_inv_p);
+    const double ivy = is_move ? dmul(dmul(f, fy), m_inv_p) : dmul(pfy, m_inv_p);
+    const double nvx = dadd(pvx, ivx), nvy = dadd(pvy, ivy);
+    if (is_move || is_press) { L.f(po + kVX) = nvx; L.f(po + kVY) = nvy; }
+    if (is_move && touch) { L.f(bo + kVX) = nvx; L.f(bo + kVY) = nvy; }  // _ball_move_with_player, :300-304
+    if ((key == 2 || key == 4) && touch) {                               // shoot :344-366, pass :394-416
+        double gx, gy, force, div;
+        if (key == 2) { gx = side == 0 ? kWidth : 0.0; gy = kHeight / 2; force = kBallForce; div = 2.0; }
+        else {
+            const int tg = pass_target(L, P, env_id, s.t_total, j, p, arrow);
+            gx = L.f(tg * kBodyStride + kPX); gy = L.f(tg * kBodyStride + kPY); force = kBallForce - 20; div = 10.0;
         }
-    } else {                                                             // press :371-391
-        if (!touch && arrow == 0) {
-            const double vx = dsub(L.f(bo + kPX), L.f(po + kPX)), vy = dsub(L.f(bo + kPY), L.f(po + kPY));
-            const double mag = dsqrt(dadd(dmul(vx, vx), dmul(vy, vy)));
-            const double pfx = ddiv(dmul(kPlayerForce, vx), mag), pfy = ddiv(dmul(kPlayerForce, vy), mag);
-            L.f(po + kVX) = dadd(L.f(po + kVX), dmul(pfx, m_inv_p));
-            L.f(po + kVY) = dadd(L.f(po + kVY), dmul(pfy, m_inv_p));
-        }
+        const double vx = dsub(gx, L.f(bo + kPX)), vy = dsub(gy, L.f(bo + kPY));
+        const double kmag = dsqrt(dadd(dmul(vx, vx), dmul(vy, vy)));
+        const double bfx = ddiv(dmul(force, vx), kmag), bfy = ddiv(dmul(force, vy), kmag);
+        L.f(bo + kVX) = dadd(ddiv(L.f(bo + kVX), div), dmul(bfx, m_inv_b));
+        L.f(bo + kVY) = dadd(ddiv(L.f(bo + kVY), div), dmul(bfy, m_inv_b));
     }
-    if (touch) s.owner_side = side;                                      // :450-451
+    if (touch) s.owner_side = side;                                      // :364, :414, :450-451
 }
 
 // closest point of segment s to (cx, cy): every segment is axis-aligned, so it is the centre's coordinate
@@ -270,6 +301,7 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
     const double m_inv_p = 1.0 / kPlayerWeight, m_inv_b = 1.0 / kBallWeight;
     int nc = 0;
     // 1. integrate positions (cpBodyUpdatePosition): p += (v + v_bias) dt; v_bias = 0
+#pragma unroll 1
     for (int i = 0; i < B; ++i) {
         const int o = i * kBodyStride;
         L.f(o + kPX) = dadd(L.f(o + kPX), dmul(dadd(L.f(o + kVX), L.f(o + kBX)), kDt));
@@ -279,7 +311,9 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
     // 2. narrow phase in pair-id order + 5. arbiter pre-step (uses the velocities before step 6)
     //    pass 0: circle/circle pairs (i < j), id j(j-1)/2 + i: outer loop over j, inner over i;
     //    pass 1: circle/segment pairs, id CC + 12 * body + segment
+#pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
         for (int jb = pass == 0 ? 1 : 0; jb < B; ++jb) {
             const int inner = pass == 0 ? jb : kNSeg;
             const int bo_j = jb * kBodyStride;
@@ -289,6 +323,7 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
                 // border, and r + r_segment <= 2.5
                 if (jx_ > 2.5 && jx_ < kWidth - 2.5 && jy_ > 2.5 && jy_ < kHeight - 2.5) continue;
             }
+#pragma unroll 1
             for (int ii = 0; ii < inner; ++ii) {
                 int a, b, q;                                             // b < 0: static segment -1 - b
                 if (pass == 0) { a = ii; b = jb; q = jb * (jb - 1) / 2 + ii; }
@@ -334,14 +369,17 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
         }
     }
     // 6. integrate velocities through velocity_func (player.py:45-50, ball.py:49-54)
+#pragma unroll 1
     for (int i = 0; i < B; ++i) {
         const int o = i * kBodyStride;
         double vx = dadd(dmul(L.f(o + kVX), P.damping_dt), 0.0), vy = dadd(dmul(L.f(o + kVY), P.damping_dt), 0.0);
-        const double l = dsqrt(dadd(dmul(vx, vx), dmul(vy, vy))), mx = i == ball ? kBallMaxV : kPlayerMaxV;
+        const double l2 = dadd(dmul(vx, vx), dmul(vy, vy));
+        const double lr = dsqrt(pick(l2 != 0.0, l2, 1.0)), l = l2 != 0.0 ? lr : 0.0, mx = i == ball ? kBallMaxV : kPlayerMaxV;
         if (l > mx) { const double sc = ddiv(mx, l); vx = dmul(vx, sc); vy = dmul(vy, sc); }
         L.f(o + kVX) = vx; L.f(o + kVY) = vy;
     }
     // 7. warm start (cpArbiterApplyCachedImpulse, dt_coef = 1)
+#pragma unroll 1
     for (int i = 0; i < nc; ++i) {
         const Contact &k = con[i];
         const double jx = dmul(k.nx, k.jn), jy = dmul(k.ny, k.jn), ma = k.a == ball ? m_inv_b : m_inv_p;
@@ -354,7 +392,9 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
         }
     }
     // 8. ten iterations of cpArbiterApplyImpulse over the contacts in order
+#pragma unroll 1
     for (int it = 0; it < 10; ++it) {
+#pragma unroll 1
         for (int i = 0; i < nc; ++i) {
             Contact &k = con[i];
             const int a = k.a, b = k.b, ao = a * kBodyStride, bo = (b >= 0 ? b : 0) * kBodyStride;
@@ -389,7 +429,7 @@ struct StepResult { double reward; int done; int flags; int contacts; int overfl
 // Futbol.step, :427-483.  `left`: this env's 2N action bytes (arrow, key per left player) or nullptr =
 // synthetic uniform actions from Philox stream 1.
 __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id, const uint8_t *left,
-                                              const PairCache &C, Contact *con)
+                                              const PairCache &C, Contact *con, uint32_t form_base)
 {
     const int N = P.n_players, ball = 2 * N, bo = ball * kBodyStride;
     StepResult res;
@@ -397,12 +437,14 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
     uint32_t j = 0;                                                      // sequential dynamics draws of this step
     double init_d[kMaxN];                                                // :433
     const double bix = L.f(bo + kPX), biy = L.f(bo + kPY);               // :435
+#pragma unroll 1
     for (int i = 0; i < N; ++i) {
         const double dx = dsub(L.f(i * kBodyStride + kPX), bix), dy = dsub(L.f(i * kBodyStride + kPY), biy);
         init_d[i] = dsqrt(dadd(dmul(dx, dx), dmul(dy, dy)));
     }
     double reward = 0.0;
 
+#pragma unroll 1
     for (int p = 0; p < 2 * N; ++p) {                                    // :447-453, right team = action_space.sample() (:429)
         int arrow, key;
         if (p < N && left != nullptr) { arrow = left[2 * p] % 5; key = left[2 * p + 1] % 5; }
@@ -417,6 +459,7 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
     }
 
     bool out = false;                                                    // check_and_fix_out_bounds, :256-287
+#pragma unroll 1
     for (int sg = 0; sg < 6 && !out; ++sg) {
         if (!ball_touches_segment(L, ball, sg)) continue;
         out = true;
@@ -450,11 +493,13 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
     }
 
     bool goal = false;                                                   // ball_contact_goal, :291-296
+#pragma unroll 1
     for (int sg = 6; sg < 12; ++sg) goal = goal || ball_touches_segment(L, ball, sg);
     if (goal) {                                                          // :469-475
         const bool left_scored = L.f(bo + kPX) > kWidth - 2;
         reward = dadd(reward, left_scored ? 1000.0 : -1000.0);
-        position_to_initial(L, s, P);
+        position_to_initial(L, N, form_base);
+        s.stamp += 1;
         s.owner_side = (int)__umulhi(draw(P, env_id, s.t_total, j), 2u);
         res.flags |= kFlagGoal | (left_scored ? (int)kFlagGoalLeft : 0);
     }

@@ -37,6 +37,7 @@ void host_v1_rollout(uint64_t seed, uint32_t env_id0, int n_players, int ep_limi
     for (int i = 0; i < 2 * n_players; ++i) { P.form_x[i] = form_x[i]; P.form_y[i] = form_y[i]; }
     const int N = n_players, B = 2 * N + 1, D = 4 + 8 * N, NP = n_pairs(B);
     const Lane L = make_lane(0, 0, N);
+    const uint32_t form_base = stage_formation(P, 1, 0, 1);
     std::vector<double> jn(NP);
     std::vector<uint32_t> last(NP);
     Contact con[kMaxContacts];
@@ -46,11 +47,11 @@ void host_v1_rollout(uint64_t seed, uint32_t env_id0, int n_players, int ep_limi
         PairCache C{jn.data(), last.data(), 1};
         V1Regs s;
         const uint32_t env_id = env_id0 + (uint32_t)i;
-        init_env(L, s, P, env_id);
+        init_env(L, s, P, env_id, form_base);
         for (int k = 0; k < steps; ++k) {
             const size_t slot = (size_t)k * n + i;
-            const StepResult r = v1_step(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con);
-            if (r.done) reset_env(L, s, P, env_id);
+            const StepResult r = v1_step(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con, form_base);
+            if (r.done) reset_env(L, s, P, env_id, form_base);
             if (obs) for (int e = 0; e < D; ++e) obs[slot * D + e] = obs_elem(L, N, e);
             if (reward) reward[slot] = r.reward;
             if (done) done[slot] = (uint8_t)r.done;
