@@ -198,7 +198,10 @@ __device__ __forceinline__ double obs_elem(Lane L, int N, int k)
     const double v = L.f(body * kBodyStride + fld * kLanes);
     const double avg = fld == 0 ? 52.5 : (fld == 1 ? 34.0 : 0.0);
     const double rng = fld == 0 ? (k < 4 ? 52.5 : 55.5) : (fld == 1 ? 34.0 : (k < 4 ? 25.0 : 10.0));
-    return ddiv(dsub(v, avg), rng);
+    const double num = dsub(v, avg);
+    const bool z = num == 0.0;                                           // 0 / rng = that same zero: keep it off the divider's slow path
+    const double q = ddiv(pick(z, 1.0, num), rng);
+    return z ? num : q;
 }
 
 __device__ __forceinline__ bool touching(Lane L, int p, int ball)
