@@ -11,6 +11,11 @@
 
 using namespace futbol;
 
+namespace futbol {
+cudaError_t launch_gae(const float *reward, const uint8_t *done, const float *value, float gamma, float lam, float *adv,
+                       float *ret, int T, int n, cudaStream_t st);
+}
+
 struct FutbolHandle {
     FutbolConfig cfg;
     V0Params v0;
@@ -197,6 +202,17 @@ int futbol_rollout(FutbolHandle *h, void *state, int K, const uint8_t *actions, 
                              : v0_launch_rollout(h->v0, state, K, actions, obs, reward, done, stats, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     h->launches += 1;
+    return FUTBOL_OK;
+}
+
+int futbol_gae(const float *reward, const uint8_t *done, const float *value, float gamma, float lam, float *adv, float *ret,
+               int T, int n, void *stream)
+{
+    if (reward == nullptr || done == nullptr || value == nullptr || adv == nullptr || ret == nullptr)
+        return fail(FUTBOL_ERR_ARG, "null argument%s");
+    if (T <= 0 || n <= 0) return fail(FUTBOL_ERR_ARG, "T and n must be positive%s");
+    cudaError_t e = launch_gae(reward, done, value, gamma, lam, adv, ret, T, n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
     return FUTBOL_OK;
 }
 

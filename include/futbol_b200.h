@@ -130,6 +130,14 @@ size_t futbol_env_state_bytes(const FutbolHandle *h); /* sizeof one AoS record *
 int futbol_get_state(FutbolHandle *h, const void *state, void *aos_out, void *stream);
 int futbol_set_state(FutbolHandle *h, void *state, const void *aos_in, void *stream); /* v0 only */
 
+/* ---- rollout-buffer glue: generalised advantage estimation -----------------------------
+ * The consumer directly behind the path in the reference's flow (stable-baselines PPO2 runner,
+ * colab_notebook.ipynb:852).  reward float32 [T, n], done uint8 [T, n] (done_t: the episode ended AT
+ * step t, so nothing is bootstrapped across it), value float32 [T + 1, n] (V of obs_t; row T = V of the
+ * observation after the last step); adv, ret float32 [T, n].  No handle: a pure function of its inputs. */
+int futbol_gae(const float *reward, const uint8_t *done, const float *value, float gamma, float lam,
+               float *adv, float *ret, int T, int n, void *stream);
+
 /* number of kernels this handle has launched (bench.py's gpu_launches) */
 uint64_t futbol_launch_count(const FutbolHandle *h);
 
