@@ -359,7 +359,10 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
                 k.n_mass = ddiv(1.0, dadd(ma, mb));
                 double m = dadd(pen, kSlop);
                 m = m < 0.0 ? m : 0.0;                                   // cpfmin(0, dist + slop)
-                k.bias = ddiv(dmul(-P.bias_coef, m), kDt);
+                const double bnum = dmul(-P.bias_coef, m);               // -0.0 unless the pair overlaps by more than the slop
+                const bool bz = bnum == 0.0;
+                const double bq = ddiv(pick(bz, 1.0, bnum), kDt);
+                k.bias = bz ? bnum : bq;                                 // 0 / dt = that same zero, kept off the divider's slow path
                 k.jbias = 0.0;
                 const double vbx = b >= 0 ? L.f(b * kBodyStride + kVX) : 0.0, vby = b >= 0 ? L.f(b * kBodyStride + kVY) : 0.0;
                 const double el = b >= 0 ? kElasticity * kElasticity : kElasticity * 0.0;
