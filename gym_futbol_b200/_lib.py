@@ -43,7 +43,7 @@ STATS_DTYPE = np.dtype([("reward_sum", np.float64), ("env_steps", np.uint64), ("
 EXPORTS = ("futbol_create", "futbol_destroy", "futbol_last_error", "futbol_abi_version", "futbol_state_bytes",
            "futbol_obs_dim", "futbol_act_dim", "futbol_draw_limit_steps", "futbol_reset", "futbol_step",
            "futbol_rollout", "futbol_env_state_bytes", "futbol_get_state", "futbol_set_state",
-           "futbol_launch_count", "futbol_gae")
+           "futbol_launch_count", "futbol_gae", "futbol_selftest_arith")
 
 _lib = None
 
@@ -100,6 +100,8 @@ def load():
     L.futbol_get_state.argtypes = [vp, vp, vp, vp]
     L.futbol_set_state.restype = C.c_int
     L.futbol_set_state.argtypes = [vp, vp, vp, vp]
+    L.futbol_selftest_arith.restype = C.c_int
+    L.futbol_selftest_arith.argtypes = [vp, vp, vp, C.c_size_t, vp]
     L.futbol_gae.restype = C.c_int
     L.futbol_gae.argtypes = [vp, vp, vp, C.c_float, C.c_float, vp, vp, C.c_int, C.c_int, vp]
     if L.futbol_abi_version() != ABI_VERSION:

@@ -12,6 +12,7 @@
 using namespace futbol;
 
 namespace futbol {
+cudaError_t launch_selftest_arith(const double *a, const double *b, unsigned long long *mismatch, size_t n, cudaStream_t st);
 cudaError_t launch_gae(const float *reward, const uint8_t *done, const float *value, float gamma, float lam, float *adv,
                        float *ret, int T, int n, cudaStream_t st);
 }
@@ -212,6 +213,14 @@ int futbol_gae(const float *reward, const uint8_t *done, const float *value, flo
         return fail(FUTBOL_ERR_ARG, "null argument%s");
     if (T <= 0 || n <= 0) return fail(FUTBOL_ERR_ARG, "T and n must be positive%s");
     cudaError_t e = launch_gae(reward, done, value, gamma, lam, adv, ret, T, n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    return FUTBOL_OK;
+}
+
+int futbol_selftest_arith(const double *a, const double *b, uint64_t *mismatch, size_t n, void *stream)
+{
+    if (a == nullptr || b == nullptr || mismatch == nullptr || n == 0) return fail(FUTBOL_ERR_ARG, "null argument%s");
+    cudaError_t e = launch_selftest_arith(a, b, (unsigned long long *)mismatch, n, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     return FUTBOL_OK;
 }

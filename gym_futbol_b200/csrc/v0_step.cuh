@@ -25,6 +25,7 @@
 #pragma once
 #include <stdint.h>
 #include "philox.cuh"
+#include "ieee_fast.cuh"
 
 namespace futbol {
 
@@ -119,7 +120,8 @@ __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a,
 // c ? a : b that the optimiser cannot look through.  Used where a lane is handed a benign operand to keep
 // it on the fast path of the IEEE sqrt/div sequence: with a plain ternary the compiler rewrites
 // sqrt(c ? q : 1.0) into c ? sqrt(q) : 1.0 and the zero operand is back (seen in ncu as 1-6 lanes per warp
-// inside __cuda_sm20_dsqrt_rn_f64_mediumpath / div_rn_f64_full on every step).
+// inside __cuda_sm20_dsqrt_rn_f64_mediumpath / div_rn_f64_full on every step).  The hot-path operations now use
+// the guard-free sequences of ieee_fast.cuh, for which the benign operand is a REQUIREMENT (fsqrt(0) is not 0).
 #ifndef FUTBOL_HOST_SHIM
 __device__ __forceinline__ double pick(bool c, double a, double b)
 {
@@ -253,11 +255,11 @@ __device__ __forceinline__ void player_turn(Lane L, uint32_t &j, V0Regs &s, cons
     // and the exact result (0) is selected afterwards.
     const double q = sqsum(vx, vy);
     const bool q_zero = q == 0.0;
-    const double root = __dsqrt_rn(pick((nb_int || hb_assist) && !q_zero, q, 1.0));
+    const double root = fsqrt(pick((nb_int || hb_assist) && !q_zero, q, 1.0));
     const double mag = q_zero ? 0.0 : root;
 
     // has-ball assist, :413-416
-    const double quot = ddiv(pick(hb_assist && !q_zero, mag, 1.0), kStepSize);
+    const double quot = fdiv(pick(hb_assist && !q_zero, mag, 1.0), kStepSize);
     double pass = q_zero ? 0.0 : quot;
     pass = pass > 20.0 ? 20.0 : pass;
     const double lo = dsub(pass, 1.0), hi = dadd(pass, 1.0);
@@ -361,10 +363,11 @@ static __device__ __noinline__ void advance_row(Lane L, int src, int dx, int dy)
     const double x = L.f(src + kX), y = L.f(src + kY), tx = L.f(src + kTX), ty = L.f(src + kTY), sp = L.f(src + kSP);
     const double s2 = sqsum(tx, ty);                                     // :562; sqrt(s2) == 0 <=> s2 == 0
     const bool moving = s2 != 0.0;
-    const double mag = __dsqrt_rn(pick(moving, s2, 1.0));
+    const double mag = fsqrt(pick(moving, s2, 1.0));
     const double nx = dmul(tx, kStepSize), ny = dmul(ty, kStepSize);
     const bool zx = nx == 0.0, zy = ny == 0.0;
-    const double qx = ddiv(pick(zx, mag, nx), mag), qy = ddiv(pick(zy, mag, ny), mag);
+    double qx, qy;
+    fdiv2(pick(zx, mag, nx), pick(zy, mag, ny), mag, qx, qy);                 // one refined reciprocal for both components
     const double x1 = dadd(x, dmul(sp, zx ? nx : qx));                   // :567
     const double y1 = dadd(y, dmul(sp, zy ? ny : qy));                   // :568
     L.f(dx) = moving ? x1 : x;
@@ -455,8 +458,8 @@ __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params 
             const bool c2 = on && !c1 && q2 <= P.reach_sq_max;
             const double qs = c1 ? q1 : q2;
             const bool live = (c1 || c2) && qs != 0.0;                   // others: benign operand, result unused
-            const double ms = __dsqrt_rn(pick(live, qs, 1.0));
-            const double sp = qs == 0.0 ? 0.0 : ddiv(pick(live, ms, 1.0), kStepSize);
+            const double ms = fsqrt(pick(live, qs, 1.0));
+            const double sp = qs == 0.0 ? 0.0 : fdiv(pick(live, ms, 1.0), kStepSize);
             if (c1 || c2) {
                 const int ro = (c1 ? kOpp1 : kOpp2) * kRowStride;
                 L.f(ro + kTX) = c1 ? v1x : v2x; L.f(ro + kTY) = c1 ? v1y : v2y; L.f(ro + kSP) = sp;

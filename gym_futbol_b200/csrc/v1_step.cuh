@@ -368,8 +368,9 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
                 const double el = b >= 0 ? kElasticity * kElasticity : kElasticity * 0.0;
                 k.bounce = dmul(dadd(dmul(dsub(vbx, L.f(ao + kVX)), k.nx), dmul(dsub(vby, L.f(ao + kVY)), k.ny)), el);
                 // cached arbiter (collision_persistence = 3): reuse the impulse of a pair that touched within 3 steps
-                const uint32_t last = C.last[(size_t)q * C.stride];
-                k.jn = (s.stamp - last <= 3u) ? C.jn[(size_t)q * C.stride] : 0.0;
+                const uint32_t last = C.last[(size_t)q * C.stride];   // both loads issued together: one HBM/L2 latency, not two
+                const double cached = C.jn[(size_t)q * C.stride];
+                k.jn = (s.stamp - last <= 3u) ? cached : 0.0;
                 C.last[(size_t)q * C.stride] = s.stamp;
             }
         }

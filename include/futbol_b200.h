@@ -138,6 +138,13 @@ int futbol_set_state(FutbolHandle *h, void *state, const void *aos_in, void *str
 int futbol_gae(const float *reward, const uint8_t *done, const float *value, float gamma, float lam,
                float *adv, float *ret, int T, int n, void *stream);
 
+/* ---- self test ----------------------------------------------------------------------------
+ * Compares the kernel's guard-free fp64 division / square-root sequences (csrc/ieee_fast.cuh) with the
+ * compiler's __ddiv_rn / __dsqrt_rn on n operand pairs: a[i] / b[i], (a[i], |b[i]|) / b[i] through the
+ * shared-reciprocal form, sqrt(|b[i]|); pairs with b[i] == 0 are skipped.  mismatch: device uint64[3]
+ * (division, two-numerator division, square root), accumulated into. */
+int futbol_selftest_arith(const double *a, const double *b, uint64_t *mismatch, size_t n, void *stream);
+
 /* number of kernels this handle has launched (bench.py's gpu_launches) */
 uint64_t futbol_launch_count(const FutbolHandle *h);
 
