@@ -59,11 +59,12 @@ __device__ __forceinline__ Philox4 philox_step_block(const PhiloxKey &K, uint32_
 
 // The sequential draws of one step.  The reference consumes a state-dependent number of draws in a
 // state-dependent order, so the position of the next draw is data.  All kDrawWords words a step can need
-// are generated up front (one rolled loop: a single copy of the ten rounds in the instruction stream) and
-// parked in this lane's shared-memory column; a draw is then one LDS at a data-dependent row.
+// are generated up front and parked in this lane's shared-memory column; a draw is then one LDS at a
+// data-dependent row.  The blocks are unrolled side by side: ten rounds are a serial chain of multiply -> xor,
+// and three independent chains interleave where one would leave the warp waiting.
 __device__ __forceinline__ void philox_fill_step(uint32_t *col, const PhiloxKey &K, uint32_t env_id, uint32_t stream, uint64_t t)
 {
-#pragma unroll 1
+#pragma unroll
     for (int b = 0; b < kSeqBlocks; ++b) {
         const Philox4 p = philox_step_block(K, env_id, stream, t, (uint32_t)b);
         uint32_t *dst = col + 4 * b * kLanes;

@@ -41,7 +41,10 @@ __host__ __device__ inline StateView make_view(void *base, int n)
     return v;
 }
 
-constexpr int kEnvThreads = 128;                                  // threads per block of every env kernel
+#ifndef FUTBOL_ENV_THREADS
+#define FUTBOL_ENV_THREADS 128
+#endif
+constexpr int kEnvThreads = FUTBOL_ENV_THREADS;                   // threads per block of every env kernel
 constexpr int kEnvSmemBytes = (kEnvThreads / 32) * kWarpSmemBytes;   // dynamic shared memory per block
 
 __device__ __forceinline__ void load_state(const StateView &v, int i, Lane L, V0Regs &s)

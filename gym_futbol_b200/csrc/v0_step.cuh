@@ -70,15 +70,17 @@ struct V0Params {
 
 // ---- per-environment working storage in shared memory ---------------------------------------------------
 // One block of kWarpSmemBytes per warp; element k of lane l of a section at section[k * kLanes + l].
-//   double  st[27][kLanes]   k = 5 * row + field, rows ai_1, ai_2, opp_1, opp_2, ball; fields x, y, tx, ty,
-//                            speed (= observation rows 0-4);  k = 25, 26: the ball's anticipated (x, y)
-//   then, overlapping in time:  uint32 draws[kDrawWords][kLanes]   (during the step)
+//   double  st[25][kLanes]   k = 5 * row + field, rows ai_1, ai_2, opp_1, opp_2, ball; fields x, y, tx, ty,
+//                            speed (= observation rows 0-4)
+//   then, overlapping in time:  uint32 draws[kDrawWords][kLanes] + double nb[2][kLanes] (during the step: the
+//                               Philox words and the ball's anticipated (x, y))
 //                               float  stage[kLanes * 30]          (observation staging, after the step)
-constexpr int kStateWords = 27;
-constexpr int kNbX = 25, kNbY = 26;
+constexpr int kStateWords = 25;
 constexpr int kObsDim = 30;
 constexpr int kWarpStateBytes = kStateWords * kLanes * 8;
-constexpr int kWarpScratchBytes = (kLanes * kObsDim * 4 > kDrawWords * kLanes * 4) ? kLanes * kObsDim * 4 : kDrawWords * kLanes * 4;
+constexpr int kNbX = kStateWords + kDrawWords / 2, kNbY = kNbX + 1;       // element index (x kLanes) of the anticipated ball
+constexpr int kStepScratchBytes = kDrawWords * kLanes * 4 + 2 * kLanes * 8;
+constexpr int kWarpScratchBytes = (kLanes * kObsDim * 4 > kStepScratchBytes) ? kLanes * kObsDim * 4 : kStepScratchBytes;
 constexpr int kWarpSmemBytes = kWarpStateBytes + kWarpScratchBytes;
 constexpr int kX = 0, kY = kLanes, kTX = 2 * kLanes, kTY = 3 * kLanes, kSP = 4 * kLanes;   // field offsets in a row
 constexpr int kRowStride = 5 * kLanes;
@@ -354,11 +356,10 @@ __device__ __forceinline__ int easy_action(Lane L, uint32_t &j, int a, bool has_
     return has_ball ? with_ball : without;
 }
 
-// _step_by_observation, :560-571 (DECELERATION = 0: the ball's speed update is `sp -= 0.0`): reads row
-// `src`, writes the new (x, y) to elements (dx, dy).  Straight-line: a stopped row (|t| == 0, :563) and a
-// zero component (0 / mag = that same signed zero) are fed benign operands so that every lane stays on the
-// fast path of sqrt/div.  Out of line: called from the kinematics loop and from the opponents' anticipation.
-static __device__ __noinline__ void advance_row(Lane L, int src, int dx, int dy)
+// _step_by_observation, :560-571 (DECELERATION = 0: the ball's speed update is `sp -= 0.0`) for one row: reads
+// row `src`, returns the new (x, y).  Straight-line: a stopped row (|t| == 0, :563) and a zero component
+// (0 / mag = that same signed zero) are fed benign operands (a requirement of the guard-free sqrt/div).
+__device__ __forceinline__ void advance_xy(Lane L, int src, double &xo, double &yo)
 {
     const double x = L.f(src + kX), y = L.f(src + kY), tx = L.f(src + kTX), ty = L.f(src + kTY), sp = L.f(src + kSP);
     const double s2 = sqsum(tx, ty);                                     // :562; sqrt(s2) == 0 <=> s2 == 0
@@ -367,11 +368,31 @@ static __device__ __noinline__ void advance_row(Lane L, int src, int dx, int dy)
     const double nx = dmul(tx, kStepSize), ny = dmul(ty, kStepSize);
     const bool zx = nx == 0.0, zy = ny == 0.0;
     double qx, qy;
-    fdiv2(pick(zx, mag, nx), pick(zy, mag, ny), mag, qx, qy);                 // one refined reciprocal for both components
+    fdiv2(pick(zx, mag, nx), pick(zy, mag, ny), mag, qx, qy);            // one refined reciprocal for both components
     const double x1 = dadd(x, dmul(sp, zx ? nx : qx));                   // :567
     const double y1 = dadd(y, dmul(sp, zy ? ny : qy));                   // :568
-    L.f(dx) = moving ? x1 : x;
-    L.f(dy) = moving ? y1 : y;
+    xo = moving ? x1 : x;
+    yo = moving ? y1 : y;
+}
+
+// The kinematics phase, :661-663: all five rows in one straight-line block (independent rows: the scheduler is
+// free to overlap their sqrt / reciprocal chains).
+__device__ __forceinline__ void advance_all(Lane L)
+{
+    double nx[5], ny[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) advance_xy(L, r * kRowStride, nx[r], ny[r]);
+#pragma unroll
+    for (int r = 0; r < 5; ++r) { L.f(r * kRowStride + kX) = nx[r]; L.f(r * kRowStride + kY) = ny[r]; }
+}
+
+// single row, out of line: the opponents' anticipation of the ball (:962-965)
+static __device__ __noinline__ void advance_row(Lane L, int src, int dx, int dy)
+{
+    double xo, yo;
+    advance_xy(L, src, xo, yo);
+    L.f(dx) = xo;
+    L.f(dy) = yo;
 }
 
 __device__ __forceinline__ bool out_of_pitch(double x, double y)
@@ -468,9 +489,8 @@ __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params 
     }
     if (shot.shooter >= 0) resolve_shot(L, s, P, RANDOM_OPP, env_id, shot);
 
-    // ---- kinematics, :661-663: one copy of the code over the five rows ----
-#pragma unroll 1
-    for (int r = 0; r < 5; ++r) advance_row(L, r * kRowStride, r * kRowStride + kX, r * kRowStride + kY);
+    // ---- kinematics, :661-663 ----
+    advance_all(L);
 
     // ---- _get_reward, :752-861 (evaluated before the goal re-kickoff) ----
     const double ball_x = L.f(bo + kX), ball_y = L.f(bo + kY);
