@@ -19,6 +19,7 @@
 #pragma once
 #include <stdint.h>
 #include "philox.cuh"
+#include "ieee_fast.cuh"
 
 namespace futbol {
 namespace v1 {
@@ -129,6 +130,14 @@ __device__ __forceinline__ double pick(bool c, double a, double b)
 inline double pick(bool c, double a, double b) { return c ? a : b; }
 #endif
 
+// sqrt for the hot path: the guard-free sequence of ieee_fast.cuh with the zero operand selected around it
+__device__ __forceinline__ double sqrt0(double x)
+{
+    const bool nz = x != 0.0;
+    const double r = fsqrt(pick(nz, x, 1.0));
+    return nz ? r : 0.0;
+}
+
 // One Philox word for the rare draws (pass target, out-of-bounds receiver, side after a goal / reset): out of line
 // and keyed by the seed (the round keys are re-derived) so that the hot loop carries a single inlined Philox.
 static __device__ __noinline__ uint32_t philox_word_cold(uint64_t seed, uint32_t env_id, uint32_t stream, uint64_t t, uint32_t block, uint32_t w)
@@ -200,7 +209,7 @@ __device__ __forceinline__ double obs_elem(Lane L, int N, int k)
     const double rng = fld == 0 ? (k < 4 ? 52.5 : 55.5) : (fld == 1 ? 34.0 : (k < 4 ? 25.0 : 10.0));
     const double num = dsub(v, avg);
     const bool z = num == 0.0;                                           // 0 / rng = that same zero: keep it off the divider's slow path
-    const double q = ddiv(pick(z, 1.0, num), rng);
+    const double q = fdiv(pick(z, 1.0, num), rng);
     return z ? num : q;
 }
 
@@ -254,8 +263,9 @@ __device__ __forceinline__ void process_action(Lane L, V1Regs &s, const V1Params
     const bool is_move = key <= 1;                                       // noop :331-335, dash :338-341
     const bool is_press = key == 3 && !touch && arrow == 0;              // press :371-391 (not touching: d2 >= 6.25 > 0)
     const double f = key == 0 ? kPlayerWeight : kPlayerForce;
-    const double mag = dsqrt(pick(is_press, d2, 1.0));
-    const double pfx = ddiv(dmul(kPlayerForce, pick(is_press, dx, 1.0)), mag), pfy = ddiv(dmul(kPlayerForce, pick(is_press, dy, 1.0)), mag);
+    const double mag = fsqrt(pick(is_press, d2, 1.0));
+    double pfx, pfy;
+    fdiv2(dmul(kPlayerForce, pick(is_press, dx, 1.0)), dmul(kPlayerForce, pick(is_press, dy, 1.0)), mag, pfx, pfy);
     // apply_impulse_at_local_point: v += j * m_inv
     const double ivx = is_move ? dmul(dmul(f, fx), m_inv_p) : dmul(pfx, m_inv_p);
     const double ivy = is_move ? dmul(dmul(f, fy), m_inv_p) : dmul(pfy, m_inv_p);
@@ -381,8 +391,8 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
         const int o = i * kBodyStride;
         double vx = dadd(dmul(L.f(o + kVX), P.damping_dt), 0.0), vy = dadd(dmul(L.f(o + kVY), P.damping_dt), 0.0);
         const double l2 = dadd(dmul(vx, vx), dmul(vy, vy));
-        const double lr = dsqrt(pick(l2 != 0.0, l2, 1.0)), l = l2 != 0.0 ? lr : 0.0, mx = i == ball ? kBallMaxV : kPlayerMaxV;
-        if (l > mx) { const double sc = ddiv(mx, l); vx = dmul(vx, sc); vy = dmul(vy, sc); }
+        const double l = sqrt0(l2), mx = i == ball ? kBallMaxV : kPlayerMaxV;
+        if (l > mx) { const double sc = fdiv(mx, l); vx = dmul(vx, sc); vy = dmul(vy, sc); }
         L.f(o + kVX) = vx; L.f(o + kVY) = vy;
     }
     // 7. warm start (cpArbiterApplyCachedImpulse, dt_coef = 1)
@@ -447,7 +457,7 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
 #pragma unroll 1
     for (int i = 0; i < N; ++i) {
         const double dx = dsub(L.f(i * kBodyStride + kPX), bix), dy = dsub(L.f(i * kBodyStride + kPY), biy);
-        init_d[i] = dsqrt(dadd(dmul(dx, dx), dmul(dy, dy)));
+        init_d[i] = sqrt0(dadd(dmul(dx, dx), dmul(dy, dy)));
     }
     double reward = 0.0;
 
@@ -491,12 +501,12 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
         const double bx = L.f(bo + kPX), by = L.f(bo + kPY);
         for (int i = (N == 5 ? 3 : 0); i < N; ++i) {                     // :501-504
             const double dx = dsub(L.f(i * kBodyStride + kPX), bx), dy = dsub(L.f(i * kBodyStride + kPY), by);
-            const double diff = dsub(init_d[i], dsqrt(dadd(dmul(dx, dx), dmul(dy, dy))));
+            const double diff = dsub(init_d[i], sqrt0(dadd(dmul(dx, dx), dmul(dy, dy))));
             if (first || diff > best) { best = diff; first = false; }
         }
         reward = dadd(reward, dmul(best, 10.0));
         const double ax = dsub(bx, kWidth), ay = dsub(by, kHeight / 2), ix = dsub(bix, kWidth), iy = dsub(biy, kHeight / 2);
-        reward = dadd(reward, dmul(dsub(dsqrt(dadd(dmul(ix, ix), dmul(iy, iy))), dsqrt(dadd(dmul(ax, ax), dmul(ay, ay)))), 10.0));
+        reward = dadd(reward, dmul(dsub(sqrt0(dadd(dmul(ix, ix), dmul(iy, iy))), sqrt0(dadd(dmul(ax, ax), dmul(ay, ay)))), 10.0));
     }
 
     bool goal = false;                                                   // ball_contact_goal, :291-296
