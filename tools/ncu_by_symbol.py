@@ -6,8 +6,9 @@ LIB = os.path.join(ROOT, "gym_futbol_b200", "csrc", "libfutbol_b200.so")
 rep, sub = sys.argv[1], sys.argv[2]
 ws = float(sys.argv[3]) if len(sys.argv) > 3 else 524288.0
 tmp = tempfile.mkdtemp(); subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=tmp, check=True, capture_output=True)
-cub = [f for f in os.listdir(tmp) if os.path.getsize(os.path.join(tmp, f)) > 10000][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
+dis = []
+for cub in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin") and os.path.getsize(os.path.join(tmp, f)) > 10000):
+    dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out))); hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}; data = rows[2:]
 best = None
