@@ -154,6 +154,15 @@ class FutbolVecEnv:
         records = np.ascontiguousarray(records, dtype=_lib.V0_ENV_STATE)
         if records.shape != (self.num_envs,):
             raise ValueError("need %d state records" % self.num_envs)
+        # The kernel's fp64 division / square root are the correctly rounded fast-path sequences without the
+        # range guard (csrc/ieee_fast.cuh); they are exact for pitch-scale operands.  Anything a simulation can
+        # reach is many orders of magnitude inside these bounds; refuse the rest instead of computing on it.
+        rows = records["rows"]
+        mag = np.abs(rows)
+        if not np.isfinite(rows).all() or (mag > 1e6).any() or ((mag != 0) & (mag < 1e-60)).any():
+            raise ValueError("state values must be finite, at most 1e6 in magnitude and either zero or at least 1e-60")
+        if (records["owner"] > 4).any() or (records["last_owner"] > 4).any() or (records["ep_step"] < 0).any():
+            raise ValueError("owner / last_owner must be 0..4 and ep_step non-negative")
         aos = torch.from_numpy(records.view(np.uint8).copy()).to(self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.futbol_set_state(self._h, _ptr(self.state), _ptr(aos), self._stream()))

@@ -128,7 +128,10 @@ int futbol_rollout(FutbolHandle *h, void *state, int K, const uint8_t *actions, 
 /* ---- state access (device AoS records: FutbolV0EnvState / FutbolV1EnvState) ---------- */
 size_t futbol_env_state_bytes(const FutbolHandle *h); /* sizeof one AoS record */
 int futbol_get_state(FutbolHandle *h, const void *state, void *aos_out, void *stream);
-int futbol_set_state(FutbolHandle *h, void *state, const void *aos_in, void *stream); /* v0 only */
+/* v0 only.  Values must be pitch-scale: finite, |value| <= 1e6 and either zero or >= 1e-60 (the kernel's
+ * correctly rounded division / square root run without a range guard, csrc/ieee_fast.cuh); the Python
+ * binding validates this on the host before the call. */
+int futbol_set_state(FutbolHandle *h, void *state, const void *aos_in, void *stream);
 
 /* ---- rollout-buffer glue: generalised advantage estimation -----------------------------
  * The consumer directly behind the path in the reference's flow (stable-baselines PPO2 runner,

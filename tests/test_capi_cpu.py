@@ -34,6 +34,7 @@ def test_struct_mirrors_match_header_sizes():
     assert _lib.V0_ENV_STATE.itemsize == 224
     assert _lib.STATS_DTYPE.itemsize == C.sizeof(_lib.FutbolStats) == 64
     assert _lib.V0_ENV_STATE.fields["t_total"][1] == 200 and _lib.V0_ENV_STATE.fields["owner"][1] == 220
+    assert _lib.V1_ENV_STATE.itemsize == 21 * 6 * 8 + 24 and _lib.V1_ENV_STATE.fields["owner_side"][1] == 21 * 6 * 8 + 16
 
 
 def test_null_arguments_return_error_codes_without_a_gpu():

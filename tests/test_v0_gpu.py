@@ -323,3 +323,56 @@ def test_errors_and_dropin_surface(torch_cuda):
     e3.reset()
     flags = [e3.step(0)[2] for _ in range(14)]
     assert flags.index(True) == len(flags) - flags[::-1].index(False) and all(flags[flags.index(True):])
+
+
+def test_set_state_from_oracle_and_continue(torch_cuda):
+    """Checkpoint / restore: the oracle's mid-trajectory state is written with set_state and both continue identically."""
+    from gym_futbol_b200 import FutbolVecEnv, _lib
+    from oracle import philox
+    from oracle.v0 import OracleV0
+    n, seed, off = 160, 21, 300
+    orc = OracleV0(n, seed=seed, env_id0=off, random_opp=False, arith=0)
+    acts = philox.actions_table(seed, np.arange(off, off + n), 0, 260)
+    orc.rollout(150, actions=acts[:150], autoreset=2, n_threads=4, record=False)
+    rec = np.zeros(n, dtype=_lib.V0_ENV_STATE)
+    rec["rows"] = orc.envs["obs"][:, :5]
+    rec["t_total"] = orc.envs["t_total"]
+    rec["ep_step"] = np.rint(orc.envs["time"] * 10).astype(np.int32)
+    rec["ai_score"], rec["opp_score"] = orc.envs["ai_score"], orc.envs["opp_score"]
+    rec["owner"], rec["last_owner"] = orc.envs["owner"], orc.envs["last_owner"]
+    env = FutbolVecEnv(n, seed=seed, env_id_offset=off, random_opp=False, dtype=torch_cuda.float64)
+    env.set_state(rec)
+    back = env.get_state()
+    assert np.array_equal(back["rows"], rec["rows"]) and np.array_equal(back["owner"], rec["owner"])
+    want = orc.rollout(110, actions=acts[150:], autoreset=2, n_threads=4)
+    for t in range(110):
+        obs, rew, done, _ = env.step(torch_cuda.from_numpy(acts[150 + t]).cuda())
+        assert np.array_equal(obs.cpu().numpy(), want["obs"][t]) and np.array_equal(rew.cpu().numpy(), want["reward"][t])
+        assert np.array_equal(done.cpu().numpy(), want["done"][t])
+    bad = rec.copy()
+    bad["rows"][3, 2, 0] = np.inf
+    with pytest.raises(ValueError):
+        env.set_state(bad)
+    bad = rec.copy()
+    bad["rows"][0, 0, 2] = 1e-200
+    with pytest.raises(ValueError):
+        env.set_state(bad)
+
+
+def test_rollout_optional_outputs_and_odd_sizes(torch_cuda):
+    """Outputs can be switched off one by one; an odd env count takes the scalar-store path of the observation writer."""
+    from gym_futbol_b200 import FutbolVecEnv
+    from oracle.v0 import OracleV0
+    n, K = 95, 40
+    want = OracleV0(n, seed=4, random_opp=True, arith=0).rollout(K, actions=None, autoreset=2, n_threads=2)
+    for kw in (dict(obs=False), dict(reward=False), dict(done=False), dict()):
+        env = FutbolVecEnv(n, seed=4, random_opp=True)
+        env.reset()
+        o, r, d = env.rollout(K, **kw)
+        assert (o is None) == ("obs" in kw) and (r is None) == ("reward" in kw) and (d is None) == ("done" in kw)
+        if o is not None:
+            assert np.array_equal(o.cpu().numpy(), want["obs"].astype(np.float32))
+        if r is not None:
+            assert np.array_equal(r.cpu().numpy(), want["reward"].astype(np.float32))
+        if d is not None:
+            assert np.array_equal(d.cpu().numpy(), want["done"])
