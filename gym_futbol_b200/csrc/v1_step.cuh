@@ -328,16 +328,19 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
     for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll 1
         for (int jb = pass == 0 ? 1 : 0; jb < B; ++jb) {
-            const int inner = pass == 0 ? jb : kNSeg;
             const int bo_j = jb * kBodyStride;
             const double jx_ = L.f(bo_j + kPX), jy_ = L.f(bo_j + kPY);
-            if (pass == 1) {
-                // no segment can be touched from strictly inside the pitch: every segment lies on or outside its
-                // border, and r + r_segment <= 2.5
-                if (jx_ > 2.5 && jx_ < kWidth - 2.5 && jy_ > 2.5 && jy_ < kHeight - 2.5) continue;
-            }
+            // candidates, visited in ascending index (= ascending pair id).  Pass 0: every body i < jb.  Pass 1: only the
+            // segments that can be reached at all -- r + r_segment <= 2.5, the left-hand segments {0, 1, 6, 7, 8} lie at
+            // x <= 0, the right-hand ones {3, 4, 9, 10, 11} at x >= 105, segment 5 on y = 0 and segment 2 on y = 68 --
+            // so a body strictly inside the pitch tests none and a body at a touchline tests one.
+            uint32_t cand;
+            if (pass == 0) cand = (1u << jb) - 1u;
+            else cand = (jx_ < 2.5 ? 0x1C3u : 0u) | (jx_ > kWidth - 2.5 ? 0xE18u : 0u) | (jy_ < 2.5 ? 0x020u : 0u) | (jy_ > kHeight - 2.5 ? 0x004u : 0u);
 #pragma unroll 1
-            for (int ii = 0; ii < inner; ++ii) {
+            while (cand != 0u) {
+                const int ii = __ffs((int)cand) - 1;
+                cand &= cand - 1u;
                 int a, b, q;                                             // b < 0: static segment -1 - b
                 if (pass == 0) { a = ii; b = jb; q = jb * (jb - 1) / 2 + ii; }
                 else { a = jb; b = -1 - ii; q = CC + jb * kNSeg + ii; }
