@@ -269,7 +269,6 @@ def main():
         b.record(stream)
     t_end.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     launches = env.launch_count - launches0
     elapsed_ms = t_start.elapsed_time(t_end)
     kernel_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
@@ -359,6 +358,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     resident_value = args.envs * K * e2e_steps / (t.item() * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None      # sampled across all three timed regions (value, e2e, resident)
 
     stats = torch.from_numpy(env.stats.cpu().numpy().view("int64").copy()).to(dev)   # optional statistics gather
     if world > 1:
