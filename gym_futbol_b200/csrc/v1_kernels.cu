@@ -49,13 +49,13 @@ __host__ __device__ inline StateView make_view(void *base, int n, int n_players)
 
 __device__ __forceinline__ void load_state(const StateView &v, int i, Lane L, V1Regs &s, int B)
 {
-    for (int k = 0; k < 6 * B; ++k) L.f(k * kLanes) = v.body[(size_t)k * v.np + i];
+    for (int k = 0; k < 6 * B; ++k) L.f(k * kCol) = v.body[(size_t)k * v.np + i];
     s.t_total = v.t_total[i]; s.stamp = v.stamp[i]; s.ep_step = v.ep_step[i]; s.owner_side = v.owner_side[i];
 }
 
 __device__ __forceinline__ void store_state(const StateView &v, int i, Lane L, const V1Regs &s, int B, int flags)
 {
-    for (int k = 0; k < 6 * B; ++k) v.body[(size_t)k * v.np + i] = L.f(k * kLanes);
+    for (int k = 0; k < 6 * B; ++k) v.body[(size_t)k * v.np + i] = L.f(k * kCol);
     v.t_total[i] = s.t_total; v.stamp[i] = s.stamp; v.ep_step[i] = s.ep_step; v.owner_side[i] = (uint8_t)s.owner_side;
     v.flags[i] = (uint8_t)flags;
 }
@@ -67,25 +67,23 @@ __device__ __forceinline__ void thread_store_obs(T *dst_row, Lane L, int N)
     for (int k = 0; k < D; ++k) dst_row[k] = (T)obs_elem(L, N, k);
 }
 
-// fp32 observation rows staged per warp and written as consecutive 128-bit stores (a warp's 32 rows are one
-// contiguous span of [n, D])
-__device__ __forceinline__ void warp_store_obs_f32(Lane L, int N, float *stage, float *gdst_warp_row0, int lane, int rows_in_warp, bool vec_ok)
+// fp32 observations of a warp's 32 environments = one contiguous span of [n, D]: output element e belongs to
+// environment e / D of the warp, and every lane can read every lane's column (same warp, shared memory), so the
+// warp writes the span in order, 32 consecutive floats per instruction, without a staging copy.
+__device__ __forceinline__ void warp_store_obs_f32(Lane L, int N, float *gdst_warp_row0, int lane, int rows_in_warp)
 {
     const int D = obs_dim(N);
-    __syncwarp();
-    float *mine = stage + lane * D;
-    for (int k = 0; k < D; ++k) mine[k] = (float)obs_elem(L, N, k);
-    __syncwarp();
+    __syncwarp();                                     // every lane's step has finished writing its column
+    Lane other;
+    int env = lane / D, k = lane - env * D;
     const int total = rows_in_warp * D;
-    if (vec_ok) {
-        const int nvec = total >> 2;
-        const float4 *src = reinterpret_cast<const float4 *>(stage);
-        float4 *dst = reinterpret_cast<float4 *>(gdst_warp_row0);
-        for (int q = lane; q < nvec; q += 32) __stcs(dst + q, src[q]);
-    } else {
-        for (int q = lane; q < total; q += 32) __stcs(gdst_warp_row0 + q, stage[q]);
+    for (int e = lane; e < total; e += 32) {
+        other.st = L.st - (uint32_t)lane + (uint32_t)env;
+        __stcs(gdst_warp_row0 + e, (float)obs_elem(other, N, k));
+        k += 32;
+        while (k >= D) { k -= D; env += 1; }
     }
-    __syncwarp();
+    __syncwarp();                                     // before the next step overwrites the columns
 }
 
 template <typename T>
@@ -144,10 +142,8 @@ __global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t 
     const int rows_in_warp = min(32, P.n_envs - warp_env0);
     const int N = P.n_players, B = 2 * N + 1, D = obs_dim(N);
     const size_t n = (size_t)P.n_envs;
-    const bool vec_ok = ((n * D) % 4 == 0) && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0) && rows_in_warp == 32;
     const uint32_t env_id = P.env_id_offset + (uint32_t)i;
     const Lane L = make_lane(warp, lane, N);
-    float *stage = reinterpret_cast<float *>(futbol_smem + warp * warp_smem_bytes(N) + warp_state_bytes(N));
     // padding lanes of the last warp step env 0's cache column?  No: they get a private dummy state and never touch HBM
     const int ci = live ? i : 0;
     const PairCache C{v.jn + ci, v.last + ci, v.np};
@@ -177,7 +173,7 @@ __global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t 
         outs += (r.flags & kFlagOut) != 0;
         episodes += r.done;
         contacts += r.contacts; overflow += r.overflow;
-        if (obs != nullptr) warp_store_obs_f32(L, N, stage, obs + ((size_t)k * n + (size_t)warp_env0) * D, lane, rows_in_warp, vec_ok);
+        if (obs != nullptr) warp_store_obs_f32(L, N, obs + ((size_t)k * n + (size_t)warp_env0) * D, lane, rows_in_warp);
         if (live) {
             if (reward != nullptr) __stcs(reward + slot, (float)r.reward);
             if (done != nullptr) done[slot] = (uint8_t)r.done;
@@ -223,7 +219,7 @@ __global__ void v1_get_state_kernel(int n, int n_players, StateView v, FutbolV1E
 
 // ---- host launchers ------------------------------------------------------------------------------------
 static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
-static inline int threads_for(int n_players) { return n_players <= 5 ? 64 : 32; }   // keeps a block under 48 KB of shared memory
+static inline int threads_for(int n_players) { return n_players <= 5 ? 64 : 32; }   // keeps a block under 48 KB of shared memory (10v10: 33 KB per warp)
 static inline int smem_for(int n_players) { return block_smem_bytes(n_players, threads_for(n_players) / 32); }
 
 cudaError_t launch_reset(const V1Params &P, void *state, const uint8_t *mask, void *obs, int obs_f64, int init, cudaStream_t st)

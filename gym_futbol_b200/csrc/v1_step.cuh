@@ -72,24 +72,28 @@ struct V1Params {
 };
 
 // ---- per-environment working storage --------------------------------------------------------------------
-// shared memory, one column per lane: element (6 * body + field) of lane l at st[(6 * body + field) * kLanes + l];
+// shared memory, one column per lane: element (6 * body + field) of lane l at st[(6 * body + field) * kCol + l],
+// kCol = 33: a lane walking its own column is conflict-free (consecutive lanes, consecutive words), and so is a
+// warp reading ONE lane's column element by element (the transposed read of the observation writer: consecutive
+// elements are 33 doubles apart = 2 banks, not 0);
 // fields x, y, vx, vy, v_bias_x, v_bias_y; bodies: team A 0..N-1, team B N..2N-1, ball 2N.
 #ifndef FUTBOL_HOST_SHIM
 extern __shared__ __align__(16) unsigned char futbol_smem[];
 #else
-static unsigned char futbol_smem[8 * 6 * kMaxBodies + 4 * (4 + 8 * kMaxN) + 8 * 4 * kMaxN] __attribute__((aligned(16)));
+static unsigned char futbol_smem[8 * 6 * kMaxBodies + 16 + 8 * 4 * kMaxN] __attribute__((aligned(16)));
 #endif
-constexpr int kPX = 0, kPY = kLanes, kVX = 2 * kLanes, kVY = 3 * kLanes, kBX = 4 * kLanes, kBY = 5 * kLanes;
-constexpr int kBodyStride = 6 * kLanes;
+constexpr int kCol = kLanes == 1 ? 1 : kLanes + 1;
+constexpr int kPX = 0, kPY = kCol, kVX = 2 * kCol, kVY = 3 * kCol, kBX = 4 * kCol, kBY = 5 * kCol;
+constexpr int kBodyStride = 6 * kCol;
 
 struct Lane {
     uint32_t st;          // index (in doubles) of this lane's element 0
     __device__ __forceinline__ double &f(int k) const { return reinterpret_cast<double *>(futbol_smem)[st + k]; }
 };
 
-__host__ __device__ constexpr int warp_state_bytes(int n_players) { return 6 * (2 * n_players + 1) * kLanes * 8; }
+__host__ __device__ constexpr int warp_state_bytes(int n_players) { return ((6 * (2 * n_players + 1) * kCol * 8) + 15) & ~15; }
 __host__ __device__ constexpr int obs_dim(int n_players) { return 4 + 8 * n_players; }
-__host__ __device__ constexpr int warp_smem_bytes(int n_players) { return warp_state_bytes(n_players) + obs_dim(n_players) * kLanes * 4; }
+__host__ __device__ constexpr int warp_smem_bytes(int n_players) { return warp_state_bytes(n_players); }
 __host__ __device__ constexpr int block_smem_bytes(int n_players, int warps) { return warps * warp_smem_bytes(n_players) + 4 * n_players * 8; }
 __host__ __device__ constexpr int n_pairs(int bodies) { return bodies * (bodies - 1) / 2 + bodies * kNSeg; }
 
@@ -204,7 +208,7 @@ __device__ __forceinline__ void init_env(Lane L, V1Regs &s, const V1Params &P, u
 __device__ __forceinline__ double obs_elem(Lane L, int N, int k)
 {
     const int body = k < 4 ? 2 * N : (k - 4) >> 2, fld = k & 3;
-    const double v = L.f(body * kBodyStride + fld * kLanes);
+    const double v = L.f(body * kBodyStride + fld * kCol);
     const double avg = fld == 0 ? 52.5 : (fld == 1 ? 34.0 : 0.0);
     const double rng = fld == 0 ? (k < 4 ? 52.5 : 55.5) : (fld == 1 ? 34.0 : (k < 4 ? 25.0 : 10.0));
     const double num = dsub(v, avg);
