@@ -468,10 +468,19 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
     }
     double reward = 0.0;
 
+    // the left team's 2N action bytes, fetched up front (independent loads, one memory latency) and packed 6 bits per
+    // player; inside the sequential turn loop below they would cost one exposed HBM latency per player
+    uint64_t packed = 0;
+    if (left != nullptr) {
+        const uint16_t *pair = reinterpret_cast<const uint16_t *>(left);   // (arrow, key) of player p; 2N bytes per env: 2-byte aligned
+#pragma unroll
+        for (int p = 0; p < kMaxN; ++p)
+            if (p < N) { const uint32_t w = pair[p]; packed |= (uint64_t)(((w & 0xffu) % 5u) | ((((w >> 8) & 0xffu) % 5u) << 3)) << (6 * p); }
+    }
 #pragma unroll 1
     for (int p = 0; p < 2 * N; ++p) {                                    // :447-453, right team = action_space.sample() (:429)
         int arrow, key;
-        if (p < N && left != nullptr) { arrow = left[2 * p] % 5; key = left[2 * p + 1] % 5; }
+        if (p < N && left != nullptr) { arrow = (int)((packed >> (6 * p)) & 7u); key = (int)((packed >> (6 * p + 3)) & 7u); }
         else {
             const uint32_t stream = p < N ? kStreamActions : kStreamV1Opp;
             const int q = p < N ? p : p - N;
