@@ -104,7 +104,7 @@ __global__ void v1_reset_kernel(V1Params P, StateView v, const uint8_t *mask, T 
     if (obs != nullptr) thread_store_obs(obs + (size_t)i * obs_dim(N), L, N);
 }
 
-template <typename T>
+template <typename T, int REGC>
 __global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, T *obs, T *reward, uint8_t *done, T *final_obs)
 {
     const uint32_t form_base = stage_formation(P, blockDim.x >> 5, threadIdx.x, blockDim.x);
@@ -118,7 +118,7 @@ __global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, 
     Contact con[kMaxContacts];
     V1Regs s;
     load_state(v, i, L, s, B);
-    const StepResult r = v1_step(L, s, P, env_id, actions + (size_t)i * 2 * N, C, con, form_base);
+    const StepResult r = v1_step<REGC>(L, s, P, env_id, actions + (size_t)i * 2 * N, C, con, form_base);
     if (r.done && P.auto_reset) {
         if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * D, L, N);
         reset_env(L, s, P, env_id, form_base);
@@ -129,6 +129,7 @@ __global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, 
     if (done != nullptr) done[i] = (uint8_t)r.done;
 }
 
+template <int REGC>
 __global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t *__restrict__ actions, float *__restrict__ obs,
                                   float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
 {
@@ -161,7 +162,7 @@ __global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t 
         const size_t slot = (size_t)k * n + (size_t)i;
         StepResult r;
         if (live) {
-            r = v1_step(L, s, P, env_id, actions != nullptr ? actions + slot * 2 * N : nullptr, C, con, form_base);
+            r = v1_step<REGC>(L, s, P, env_id, actions != nullptr ? actions + slot * 2 * N : nullptr, C, con, form_base);
             if (r.done && P.auto_reset) reset_env(L, s, P, env_id, form_base);
         } else {
             r.reward = 0.0; r.done = 0; r.flags = 0; r.contacts = 0; r.overflow = 0;
@@ -220,6 +221,7 @@ __global__ void v1_get_state_kernel(int n, int n_players, StateView v, FutbolV1E
 // ---- host launchers ------------------------------------------------------------------------------------
 static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 static inline int threads_for(int n_players) { return n_players <= 5 ? 64 : 32; }   // keeps a block under 48 KB of shared memory (10v10: 33 KB per warp)
+static inline int regc_for(int n_players) { return n_players >= 4 ? 2 : 0; }   // contacts kept in registers by the solver (v1_step.cuh space_step)
 static inline int smem_for(int n_players) { return block_smem_bytes(n_players, threads_for(n_players) / 32); }
 
 cudaError_t launch_reset(const V1Params &P, void *state, const uint8_t *mask, void *obs, int obs_f64, int init, cudaStream_t st)
@@ -243,8 +245,15 @@ cudaError_t launch_step(const V1Params &P, void *state, const uint8_t *actions, 
 {
     const StateView v = make_view(state, P.n_envs, P.n_players);
     const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
-    if (out_f64) v1_step_kernel<double><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, actions, (double *)obs, (double *)reward, done, (double *)final_obs);
-    else v1_step_kernel<float><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, actions, (float *)obs, (float *)reward, done, (float *)final_obs);
+    const int g = blocks_for(P.n_envs, t);
+    const bool big = regc_for(P.n_players) == 2;
+    if (out_f64) {
+        if (big) v1_step_kernel<double, 2><<<g, t, sm, st>>>(P, v, actions, (double *)obs, (double *)reward, done, (double *)final_obs);
+        else v1_step_kernel<double, 0><<<g, t, sm, st>>>(P, v, actions, (double *)obs, (double *)reward, done, (double *)final_obs);
+    } else {
+        if (big) v1_step_kernel<float, 2><<<g, t, sm, st>>>(P, v, actions, (float *)obs, (float *)reward, done, (float *)final_obs);
+        else v1_step_kernel<float, 0><<<g, t, sm, st>>>(P, v, actions, (float *)obs, (float *)reward, done, (float *)final_obs);
+    }
     return cudaGetLastError();
 }
 
@@ -253,7 +262,8 @@ cudaError_t launch_rollout(const V1Params &P, void *state, int K, const uint8_t 
 {
     const StateView v = make_view(state, P.n_envs, P.n_players);
     const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
-    v1_rollout_kernel<<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, K, actions, obs, reward, done, stats);
+    if (regc_for(P.n_players) == 2) v1_rollout_kernel<2><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, K, actions, obs, reward, done, stats);
+    else v1_rollout_kernel<0><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, K, actions, obs, reward, done, stats);
     return cudaGetLastError();
 }
 

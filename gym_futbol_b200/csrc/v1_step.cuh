@@ -311,12 +311,61 @@ __device__ __forceinline__ bool ball_touches_segment(Lane L, int ball, int sg)
     return dadd(dmul(dx, dx), dmul(dy, dy)) < (kRBall + kRSeg) * (kRBall + kRSeg);
 }
 
+// one solver iteration for one contact (cpArbiterApplyImpulse)
+__device__ __forceinline__ void solve_contact(Lane L, Contact &k, int ball)
+{
+    const double m_inv_p = 1.0 / kPlayerWeight, m_inv_b = 1.0 / kBallWeight;
+    const int a = k.a, b = k.b, ao = a * kBodyStride, bo = (b >= 0 ? b : 0) * kBodyStride;
+    const double ma = a == ball ? m_inv_b : m_inv_p, mb = b >= 0 ? (b == ball ? m_inv_b : m_inv_p) : 0.0;
+    const double vb2x = b >= 0 ? L.f(bo + kBX) : 0.0, vb2y = b >= 0 ? L.f(bo + kBY) : 0.0;
+    const double v2x = b >= 0 ? L.f(bo + kVX) : 0.0, v2y = b >= 0 ? L.f(bo + kVY) : 0.0;
+    const double vbn = dadd(dmul(dsub(vb2x, L.f(ao + kBX)), k.nx), dmul(dsub(vb2y, L.f(ao + kBY)), k.ny));
+    const double vrn = dadd(dmul(dsub(v2x, L.f(ao + kVX)), k.nx), dmul(dsub(v2y, L.f(ao + kVY)), k.ny));
+    const double jbn = dmul(dsub(k.bias, vbn), k.n_mass), jbn_old = k.jbias;
+    const double t1 = dadd(jbn_old, jbn);
+    k.jbias = t1 > 0.0 ? t1 : 0.0;
+    const double jn = dmul(-dadd(k.bounce, vrn), k.n_mass), jn_old = k.jn;
+    const double t2 = dadd(jn_old, jn);
+    k.jn = t2 > 0.0 ? t2 : 0.0;
+    const double db = dsub(k.jbias, jbn_old), dj = dsub(k.jn, jn_old);
+    const double bx = dmul(k.nx, db), by = dmul(k.ny, db), jx = dmul(k.nx, dj), jy = dmul(k.ny, dj);
+    L.f(ao + kBX) = dsub(L.f(ao + kBX), dmul(bx, ma)); L.f(ao + kBY) = dsub(L.f(ao + kBY), dmul(by, ma));
+    L.f(ao + kVX) = dsub(L.f(ao + kVX), dmul(jx, ma)); L.f(ao + kVY) = dsub(L.f(ao + kVY), dmul(jy, ma));
+    if (b >= 0) {
+        L.f(bo + kBX) = dadd(L.f(bo + kBX), dmul(bx, mb)); L.f(bo + kBY) = dadd(L.f(bo + kBY), dmul(by, mb));
+        L.f(bo + kVX) = dadd(L.f(bo + kVX), dmul(jx, mb)); L.f(bo + kVY) = dadd(L.f(bo + kVY), dmul(jy, mb));
+    }
+}
+
+// warm start of one contact (cpArbiterApplyCachedImpulse, dt_coef = 1)
+__device__ __forceinline__ void warm_start_contact(Lane L, const Contact &k, int ball)
+{
+    const double m_inv_p = 1.0 / kPlayerWeight, m_inv_b = 1.0 / kBallWeight;
+    const double jx = dmul(k.nx, k.jn), jy = dmul(k.ny, k.jn), ma = k.a == ball ? m_inv_b : m_inv_p;
+    const int ao = k.a * kBodyStride;
+    L.f(ao + kVX) = dsub(L.f(ao + kVX), dmul(jx, ma)); L.f(ao + kVY) = dsub(L.f(ao + kVY), dmul(jy, ma));
+    if (k.b >= 0) {
+        const double mb = k.b == ball ? m_inv_b : m_inv_p;
+        const int bo = k.b * kBodyStride;
+        L.f(bo + kVX) = dadd(L.f(bo + kVX), dmul(jx, mb)); L.f(bo + kVY) = dadd(L.f(bo + kVY), dmul(jy, mb));
+    }
+}
+
 // cpSpaceStep(dt = 0.1).  Returns the number of contacts; `overflow` counts contacts beyond kMaxContacts.
+// The first two contacts of a step live in registers (c0, c1), the rest in the local-memory list `con` (index
+// i - 2): a step rarely has more than two, and the ten solver iterations would otherwise wait on local-memory
+// loads (L1 is small next to 200 KB of shared memory: ncu showed 53 % of the long-scoreboard stalls there).
+// REGC = how many contacts are register-resident: 2 for the larger teams, 0 for N <= 3 where contacts are rare and
+// the extra registers cost more occupancy than the loads cost time (measured: 2v2 -20 % with REGC = 2).
+template <int REGC>
 __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, const PairCache &C, Contact *con, int &overflow)
 {
     const int N = P.n_players, B = 2 * N + 1, ball = 2 * N, CC = B * (B - 1) / 2;
     const double m_inv_p = 1.0 / kPlayerWeight, m_inv_b = 1.0 / kBallWeight;
     int nc = 0;
+    Contact c0, c1;
+    c0.a = c0.b = c0.q = 0; c1.a = c1.b = c1.q = 0;
+    c0.nx = c0.ny = c0.n_mass = c0.bias = c0.bounce = c0.jn = c0.jbias = 0.0; c1 = c0;
     // 1. integrate positions (cpBodyUpdatePosition): p += (v + v_bias) dt; v_bias = 0
 #pragma unroll 1
     for (int i = 0; i < B; ++i) {
@@ -358,7 +407,7 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
                 const double distsq = dadd(dmul(dx, dx), dmul(dy, dy)), mind = ra + rb;
                 if (!(distsq < mind * mind)) continue;
                 if (nc == kMaxContacts) { overflow += 1; continue; }
-                Contact &k = con[nc++];
+                Contact k;
                 const double dist = dsqrt(distsq);
                 if (dist != 0.0) { const double inv = ddiv(1.0, dist); k.nx = dmul(dx, inv); k.ny = dmul(dy, inv); }
                 else if (b >= 0) { k.nx = 1.0; k.ny = 0.0; }
@@ -389,6 +438,8 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
                 const double cached = C.jn[(size_t)q * C.stride];
                 k.jn = (s.stamp - last <= 3u) ? cached : 0.0;
                 C.last[(size_t)q * C.stride] = s.stamp;
+                if (REGC > 0 && nc == 0) c0 = k; else if (REGC > 1 && nc == 1) c1 = k; else con[nc - REGC] = k;
+                nc += 1;
             }
         }
     }
@@ -403,47 +454,24 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
         L.f(o + kVX) = vx; L.f(o + kVY) = vy;
     }
     // 7. warm start (cpArbiterApplyCachedImpulse, dt_coef = 1)
+    if (REGC > 0 && nc > 0) warm_start_contact(L, c0, ball);
+    if (REGC > 1 && nc > 1) warm_start_contact(L, c1, ball);
 #pragma unroll 1
-    for (int i = 0; i < nc; ++i) {
-        const Contact &k = con[i];
-        const double jx = dmul(k.nx, k.jn), jy = dmul(k.ny, k.jn), ma = k.a == ball ? m_inv_b : m_inv_p;
-        const int ao = k.a * kBodyStride;
-        L.f(ao + kVX) = dsub(L.f(ao + kVX), dmul(jx, ma)); L.f(ao + kVY) = dsub(L.f(ao + kVY), dmul(jy, ma));
-        if (k.b >= 0) {
-            const double mb = k.b == ball ? m_inv_b : m_inv_p;
-            const int bo = k.b * kBodyStride;
-            L.f(bo + kVX) = dadd(L.f(bo + kVX), dmul(jx, mb)); L.f(bo + kVY) = dadd(L.f(bo + kVY), dmul(jy, mb));
-        }
-    }
+    for (int i = REGC; i < nc; ++i) warm_start_contact(L, con[i - REGC], ball);
     // 8. ten iterations of cpArbiterApplyImpulse over the contacts in order
+    if (nc > 0) {
 #pragma unroll 1
-    for (int it = 0; it < 10; ++it) {
+        for (int it = 0; it < 10; ++it) {
+            if (REGC > 0) solve_contact(L, c0, ball);
+            if (REGC > 1 && nc > 1) solve_contact(L, c1, ball);
 #pragma unroll 1
-        for (int i = 0; i < nc; ++i) {
-            Contact &k = con[i];
-            const int a = k.a, b = k.b, ao = a * kBodyStride, bo = (b >= 0 ? b : 0) * kBodyStride;
-            const double ma = a == ball ? m_inv_b : m_inv_p, mb = b >= 0 ? (b == ball ? m_inv_b : m_inv_p) : 0.0;
-            const double vb2x = b >= 0 ? L.f(bo + kBX) : 0.0, vb2y = b >= 0 ? L.f(bo + kBY) : 0.0;
-            const double v2x = b >= 0 ? L.f(bo + kVX) : 0.0, v2y = b >= 0 ? L.f(bo + kVY) : 0.0;
-            const double vbn = dadd(dmul(dsub(vb2x, L.f(ao + kBX)), k.nx), dmul(dsub(vb2y, L.f(ao + kBY)), k.ny));
-            const double vrn = dadd(dmul(dsub(v2x, L.f(ao + kVX)), k.nx), dmul(dsub(v2y, L.f(ao + kVY)), k.ny));
-            const double jbn = dmul(dsub(k.bias, vbn), k.n_mass), jbn_old = k.jbias;
-            const double t1 = dadd(jbn_old, jbn);
-            k.jbias = t1 > 0.0 ? t1 : 0.0;
-            const double jn = dmul(-dadd(k.bounce, vrn), k.n_mass), jn_old = k.jn;
-            const double t2 = dadd(jn_old, jn);
-            k.jn = t2 > 0.0 ? t2 : 0.0;
-            const double db = dsub(k.jbias, jbn_old), dj = dsub(k.jn, jn_old);
-            const double bx = dmul(k.nx, db), by = dmul(k.ny, db), jx = dmul(k.nx, dj), jy = dmul(k.ny, dj);
-            L.f(ao + kBX) = dsub(L.f(ao + kBX), dmul(bx, ma)); L.f(ao + kBY) = dsub(L.f(ao + kBY), dmul(by, ma));
-            L.f(ao + kVX) = dsub(L.f(ao + kVX), dmul(jx, ma)); L.f(ao + kVY) = dsub(L.f(ao + kVY), dmul(jy, ma));
-            if (b >= 0) {
-                L.f(bo + kBX) = dadd(L.f(bo + kBX), dmul(bx, mb)); L.f(bo + kBY) = dadd(L.f(bo + kBY), dmul(by, mb));
-                L.f(bo + kVX) = dadd(L.f(bo + kVX), dmul(jx, mb)); L.f(bo + kVY) = dadd(L.f(bo + kVY), dmul(jy, mb));
-            }
+            for (int i = REGC; i < nc; ++i) solve_contact(L, con[i - REGC], ball);
         }
+        if (REGC > 0) C.jn[(size_t)c0.q * C.stride] = c0.jn;
+        if (REGC > 1 && nc > 1) C.jn[(size_t)c1.q * C.stride] = c1.jn;
+#pragma unroll 1
+        for (int i = REGC; i < nc; ++i) C.jn[(size_t)con[i - REGC].q * C.stride] = con[i - REGC].jn;
     }
-    for (int i = 0; i < nc; ++i) C.jn[(size_t)con[i].q * C.stride] = con[i].jn;
     s.stamp += 1;
     return nc;
 }
@@ -452,6 +480,7 @@ struct StepResult { double reward; int done; int flags; int contacts; int overfl
 
 // Futbol.step, :427-483.  `left`: this env's 2N action bytes (arrow, key per left player) or nullptr =
 // synthetic uniform actions from Philox stream 1.
+template <int REGC>
 __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id, const uint8_t *left,
                                               const PairCache &C, Contact *con, uint32_t form_base)
 {
@@ -509,7 +538,7 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
     }
     if (out) res.flags |= kFlagOut;
 
-    res.contacts = space_step(L, s, P, C, con, res.overflow);            // :459
+    res.contacts = space_step<REGC>(L, s, P, C, con, res.overflow);            // :459
 
     if (!out) {                                                          // :463-467
         double best = 0.0;
