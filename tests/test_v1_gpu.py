@@ -106,3 +106,29 @@ def test_v1_single_env_dropin(torch_cuda):
             env.reset(); orc.reset()
     with pytest.raises(ValueError):
         env.step([0, 0, 0, 7])
+
+
+def test_v1_masked_reset_matches_oracle(torch_cuda):
+    """reset(mask) re-kicks-off only the selected envs (time 0, new side draw, arbiter cache kept) mid-episode."""
+    from gym_futbol_b200 import FutbolV1VecEnv
+    from oracle.v1 import OracleV1
+    N, n, seed = 2, 64, 13
+    env = FutbolV1VecEnv(n, number_of_player=N, seed=seed, dtype=torch_cuda.float64, auto_reset=False)
+    orc = OracleV1(n, seed=seed, number_of_player=N)
+    env.reset()
+    acts = np.random.default_rng(2).integers(0, 5, (120, n, 2 * N), dtype=np.uint8)
+    want = orc.rollout(60, actions=acts[:60], autoreset=0)
+    for t in range(60):
+        obs, _, _, _ = env.step(torch_cuda.from_numpy(acts[t]).cuda())
+    assert np.array_equal(obs.cpu().numpy(), want["obs"][-1])
+    mask = (np.arange(n) % 3 == 0).astype(np.uint8)
+    obs = env.reset(mask=torch_cuda.from_numpy(mask).cuda()).cpu().numpy()
+    orc.reset(idx=np.flatnonzero(mask))
+    ref = np.stack([orc.obs(i) for i in range(n)])
+    assert np.array_equal(obs[mask == 1], ref[mask == 1])
+    want = orc.rollout(60, actions=acts[60:], autoreset=0)
+    for t in range(60):
+        obs, rew, done, _ = env.step(torch_cuda.from_numpy(acts[60 + t]).cuda())
+        assert np.array_equal(obs.cpu().numpy(), want["obs"][t]) and np.array_equal(rew.cpu().numpy(), want["reward"][t])
+    st = env.get_state()
+    assert (st["ep_step"][mask == 1] == 60).all() and (st["ep_step"][mask == 0] == 120).all()
