@@ -43,7 +43,7 @@ STATS_DTYPE = np.dtype([("reward_sum", np.float64), ("env_steps", np.uint64), ("
 EXPORTS = ("futbol_create", "futbol_destroy", "futbol_last_error", "futbol_abi_version", "futbol_state_bytes",
            "futbol_obs_dim", "futbol_act_dim", "futbol_draw_limit_steps", "futbol_reset", "futbol_step",
            "futbol_rollout", "futbol_env_state_bytes", "futbol_get_state", "futbol_set_state",
-           "futbol_launch_count", "futbol_gae", "futbol_selftest_arith")
+           "futbol_launch_count", "futbol_gae", "futbol_selftest_arith", "futbol_step_vs", "futbol_rollout_vs")
 
 _lib = None
 
@@ -94,6 +94,10 @@ def load():
     L.futbol_reset.argtypes = [vp, vp, vp, vp, C.c_int, vp]
     L.futbol_step.restype = C.c_int
     L.futbol_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]
+    L.futbol_step_vs.restype = C.c_int
+    L.futbol_step_vs.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]
+    L.futbol_rollout_vs.restype = C.c_int
+    L.futbol_rollout_vs.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.futbol_rollout.restype = C.c_int
     L.futbol_rollout.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.futbol_get_state.restype = C.c_int

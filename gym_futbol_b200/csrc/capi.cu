@@ -180,14 +180,37 @@ int futbol_reset(FutbolHandle *h, void *state, const uint8_t *mask, void *obs, i
     return FUTBOL_OK;
 }
 
-int futbol_step(FutbolHandle *h, void *state, const uint8_t *actions, void *obs, void *reward, uint8_t *done,
-                void *final_obs, int out_dtype, void *stream)
+int futbol_step_vs(FutbolHandle *h, void *state, const uint8_t *actions, const uint8_t *opp_actions, void *obs, void *reward,
+                   uint8_t *done, void *final_obs, int out_dtype, void *stream)
 {
+    if (h != nullptr && opp_actions != nullptr && !h->is_v1 && !h->cfg.random_opp)
+        return fail(FUTBOL_ERR_ARG, "v0: opponent actions can only replace the RANDOM opponents (create with random_opp = 1)%s");
     if (h == nullptr || state == nullptr || actions == nullptr) return fail(FUTBOL_ERR_ARG, "null handle/state/actions%s");
     if (out_dtype != 0 && out_dtype != 1) return fail(FUTBOL_ERR_ARG, "out_dtype must be 0 (f32) or 1 (f64)%s");
     if (!h->initialised) return fail(FUTBOL_ERR_ARG, "futbol_reset must be called before futbol_step%s");
-    cudaError_t e = h->is_v1 ? v1::launch_step(h->v1, state, actions, obs, reward, done, final_obs, out_dtype, (cudaStream_t)stream)
-                             : v0_launch_step(h->v0, state, actions, obs, reward, done, final_obs, out_dtype, (cudaStream_t)stream);
+    cudaError_t e = h->is_v1 ? v1::launch_step(h->v1, state, actions, opp_actions, obs, reward, done, final_obs, out_dtype, (cudaStream_t)stream)
+                             : v0_launch_step(h->v0, state, actions, opp_actions, obs, reward, done, final_obs, out_dtype, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    h->launches += 1;
+    return FUTBOL_OK;
+}
+
+int futbol_step(FutbolHandle *h, void *state, const uint8_t *actions, void *obs, void *reward, uint8_t *done,
+                void *final_obs, int out_dtype, void *stream)
+{
+    return futbol_step_vs(h, state, actions, nullptr, obs, reward, done, final_obs, out_dtype, stream);
+}
+
+int futbol_rollout_vs(FutbolHandle *h, void *state, int K, const uint8_t *actions, const uint8_t *opp_actions, float *obs,
+                      float *reward, uint8_t *done, FutbolStats *stats, void *stream)
+{
+    if (h != nullptr && opp_actions != nullptr && !h->is_v1 && !h->cfg.random_opp)
+        return fail(FUTBOL_ERR_ARG, "v0: opponent actions can only replace the RANDOM opponents (create with random_opp = 1)%s");
+    if (h == nullptr || state == nullptr) return fail(FUTBOL_ERR_ARG, "null handle/state%s");
+    if (K <= 0) return fail(FUTBOL_ERR_ARG, "K must be positive%s");
+    if (!h->initialised) return fail(FUTBOL_ERR_ARG, "futbol_reset must be called before futbol_rollout%s");
+    cudaError_t e = h->is_v1 ? v1::launch_rollout(h->v1, state, K, actions, opp_actions, obs, reward, done, stats, (cudaStream_t)stream)
+                             : v0_launch_rollout(h->v0, state, K, actions, opp_actions, obs, reward, done, stats, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     h->launches += 1;
     return FUTBOL_OK;
@@ -196,14 +219,7 @@ int futbol_step(FutbolHandle *h, void *state, const uint8_t *actions, void *obs,
 int futbol_rollout(FutbolHandle *h, void *state, int K, const uint8_t *actions, float *obs, float *reward,
                    uint8_t *done, FutbolStats *stats, void *stream)
 {
-    if (h == nullptr || state == nullptr) return fail(FUTBOL_ERR_ARG, "null handle/state%s");
-    if (K <= 0) return fail(FUTBOL_ERR_ARG, "K must be positive%s");
-    if (!h->initialised) return fail(FUTBOL_ERR_ARG, "futbol_reset must be called before futbol_rollout%s");
-    cudaError_t e = h->is_v1 ? v1::launch_rollout(h->v1, state, K, actions, obs, reward, done, stats, (cudaStream_t)stream)
-                             : v0_launch_rollout(h->v0, state, K, actions, obs, reward, done, stats, (cudaStream_t)stream);
-    if (e != cudaSuccess) return cuda_fail(e);
-    h->launches += 1;
-    return FUTBOL_OK;
+    return futbol_rollout_vs(h, state, K, actions, nullptr, obs, reward, done, stats, stream);
 }
 
 int futbol_gae(const float *reward, const uint8_t *done, const float *value, float gamma, float lam, float *adv, float *ret,

@@ -121,15 +121,17 @@ __global__ void __launch_bounds__(kEnvThreads) v0_reset_kernel(V0Params P, State
 
 // ---- per-step API ----------------------------------------------------------------------------------
 template <typename T, bool RANDOM_OPP>
-__global__ void __launch_bounds__(kEnvThreads) v0_step_kernel(V0Params P, StateView v, const uint8_t *actions, T *obs,
-                                                              T *reward, uint8_t *done, T *final_obs)
+__global__ void __launch_bounds__(kEnvThreads) v0_step_kernel(V0Params P, StateView v, const uint8_t *actions,
+                                                              const uint8_t *opp_actions, T *obs, T *reward, uint8_t *done,
+                                                              T *final_obs)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_envs) return;
     const Lane L = make_lane(threadIdx.x >> 5, threadIdx.x & 31);
     V0Regs s;
     load_state(v, i, L, s);
-    const StepResult r = v0_step<RANDOM_OPP>(L, s, P, P.env_id_offset + (uint32_t)i, actions[i] & 15);
+    const StepResult r = v0_step<RANDOM_OPP>(L, s, P, P.env_id_offset + (uint32_t)i, actions[i] & 15,
+                                             opp_actions != nullptr ? (int)(opp_actions[i] & 15) : -1);
     if (r.done && P.auto_reset) {
         if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * kObsDim, L, s);
         reset_env(L, s);
@@ -147,8 +149,8 @@ __global__ void __launch_bounds__(kEnvThreads) v0_step_kernel(V0Params P, StateV
 
 template <bool RANDOM_OPP>
 __global__ void __launch_bounds__(kEnvThreads, FUTBOL_MIN_BLOCKS)
-v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ actions, float *__restrict__ obs,
-                  float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
+v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ actions, const uint8_t *__restrict__ opp_actions,
+                  float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -178,7 +180,8 @@ v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ ac
         if (actions != nullptr) a = live ? (__ldg(actions + slot) & 15) : 0;
         else a = philox_action(P.key, env_id, s.t_total, 16);
         const int ai_before = s.ai_score;
-        const StepResult r = v0_step<RANDOM_OPP>(L, s, P, env_id, a);
+        const int oa = (opp_actions != nullptr && live) ? (int)(__ldg(opp_actions + slot) & 15) : -1;
+        const StepResult r = v0_step<RANDOM_OPP>(L, s, P, env_id, a, oa);
         last_flags = r.flags;
         reward_sum += r.reward;
         goals_ai += (r.flags & kFlagGoal) && s.ai_score != ai_before;
@@ -252,34 +255,34 @@ cudaError_t v0_launch_reset(const V0Params &P, void *state, const uint8_t *mask,
 }
 
 template <typename T, bool RANDOM_OPP>
-static void launch_step(const V0Params &P, const StateView &v, const uint8_t *actions, void *obs, void *reward,
-                        uint8_t *done, void *final_obs, cudaStream_t st)
+static void launch_step(const V0Params &P, const StateView &v, const uint8_t *actions, const uint8_t *opp_actions, void *obs,
+                        void *reward, uint8_t *done, void *final_obs, cudaStream_t st)
 {
     v0_step_kernel<T, RANDOM_OPP><<<blocks_for(P.n_envs, kEnvThreads), kEnvThreads, kEnvSmemBytes, st>>>(
-        P, v, actions, (T *)obs, (T *)reward, done, (T *)final_obs);
+        P, v, actions, opp_actions, (T *)obs, (T *)reward, done, (T *)final_obs);
 }
 
-cudaError_t v0_launch_step(const V0Params &P, void *state, const uint8_t *actions, void *obs, void *reward,
-                           uint8_t *done, void *final_obs, int out_f64, cudaStream_t st)
+cudaError_t v0_launch_step(const V0Params &P, void *state, const uint8_t *actions, const uint8_t *opp_actions, void *obs,
+                           void *reward, uint8_t *done, void *final_obs, int out_f64, cudaStream_t st)
 {
     const StateView v = make_view(state, P.n_envs);
     if (out_f64) {
-        if (P.random_opp) launch_step<double, true>(P, v, actions, obs, reward, done, final_obs, st);
-        else launch_step<double, false>(P, v, actions, obs, reward, done, final_obs, st);
+        if (P.random_opp) launch_step<double, true>(P, v, actions, opp_actions, obs, reward, done, final_obs, st);
+        else launch_step<double, false>(P, v, actions, opp_actions, obs, reward, done, final_obs, st);
     } else {
-        if (P.random_opp) launch_step<float, true>(P, v, actions, obs, reward, done, final_obs, st);
-        else launch_step<float, false>(P, v, actions, obs, reward, done, final_obs, st);
+        if (P.random_opp) launch_step<float, true>(P, v, actions, opp_actions, obs, reward, done, final_obs, st);
+        else launch_step<float, false>(P, v, actions, opp_actions, obs, reward, done, final_obs, st);
     }
     return cudaGetLastError();
 }
 
-cudaError_t v0_launch_rollout(const V0Params &P, void *state, int K, const uint8_t *actions, float *obs, float *reward,
-                              uint8_t *done, FutbolStats *stats, cudaStream_t st)
+cudaError_t v0_launch_rollout(const V0Params &P, void *state, int K, const uint8_t *actions, const uint8_t *opp_actions,
+                              float *obs, float *reward, uint8_t *done, FutbolStats *stats, cudaStream_t st)
 {
     const StateView v = make_view(state, P.n_envs);
     const int blocks = blocks_for(P.n_envs, kEnvThreads);
-    if (P.random_opp) v0_rollout_kernel<true><<<blocks, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, actions, obs, reward, done, stats);
-    else v0_rollout_kernel<false><<<blocks, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, actions, obs, reward, done, stats);
+    if (P.random_opp) v0_rollout_kernel<true><<<blocks, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+    else v0_rollout_kernel<false><<<blocks, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
     return cudaGetLastError();
 }
 

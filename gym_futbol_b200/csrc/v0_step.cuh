@@ -404,8 +404,11 @@ struct StepResult { double reward; int done; int flags; };
 
 // FutbolEnv.step, :628-717.  `ai_action` in 0..15.  RANDOM_OPP = the constructor's random_opp (:138), a
 // compile-time variant so that each kernel carries only its own opponent code.
+// `opp_action`: -1 = the reference's own opponents; 0..15 (RANDOM_OPP variant only) = actions supplied by the caller
+// for opp_1 (a / 4) and opp_2 (a % 4), the self-play hook: same path as the random opponents (:642-645), the
+// randint(0, 15) draw is not taken.
 template <bool RANDOM_OPP>
-__device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params &P, uint32_t env_id, int ai_action)
+__device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params &P, uint32_t env_id, int ai_action, int opp_action = -1)
 {
     philox_fill_step(&L.draw(0), P.key, env_id, kStreamDynamics, s.t_total);
     uint32_t j = 0;
@@ -434,8 +437,9 @@ __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params 
     bool has1 = false, has2 = false, set1 = false, set2 = false, run1 = false, run2 = false;
     double t1x = -1.0, t1y = -1.0, t2x = -1.0, t2y = 1.0;
     if (RANDOM_OPP) {                                                    // :639-645
-        const int r = (int)__umulhi(L.draw(j), 16u);                     // randint(0, 15)
-        j += 1;
+        const bool given = opp_action >= 0;
+        const int r = given ? (opp_action & 15) : (int)__umulhi(L.draw(j), 16u);   // randint(0, 15)
+        j += given ? 0u : 1u;
         opp_a1 = r >> 2; opp_a2 = r & 3;
     } else {                                                             // _opp_team_set_vector_observation, :864-947
         has1 = s.owner == kOpp1; has2 = s.owner == kOpp2;                // :866-877 (latched before either acts)

@@ -105,7 +105,8 @@ __global__ void v1_reset_kernel(V1Params P, StateView v, const uint8_t *mask, T 
 }
 
 template <typename T, int REGC>
-__global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, T *obs, T *reward, uint8_t *done, T *final_obs)
+__global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, const uint8_t *opp_actions, T *obs, T *reward,
+                               uint8_t *done, T *final_obs)
 {
     const uint32_t form_base = stage_formation(P, blockDim.x >> 5, threadIdx.x, blockDim.x);
     __syncthreads();
@@ -118,7 +119,8 @@ __global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, 
     Contact con[kMaxContacts];
     V1Regs s;
     load_state(v, i, L, s, B);
-    const StepResult r = v1_step<REGC>(L, s, P, env_id, actions + (size_t)i * 2 * N, C, con, form_base);
+    const StepResult r = v1_step<REGC>(L, s, P, env_id, actions + (size_t)i * 2 * N, C, con, form_base,
+                                       opp_actions != nullptr ? opp_actions + (size_t)i * 2 * N : nullptr);
     if (r.done && P.auto_reset) {
         if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * D, L, N);
         reset_env(L, s, P, env_id, form_base);
@@ -130,7 +132,8 @@ __global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, 
 }
 
 template <int REGC>
-__global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t *__restrict__ actions, float *__restrict__ obs,
+__global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t *__restrict__ actions,
+                                  const uint8_t *__restrict__ opp_actions, float *__restrict__ obs,
                                   float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
 {
     const uint32_t form_base = stage_formation(P, blockDim.x >> 5, threadIdx.x, blockDim.x);
@@ -162,7 +165,8 @@ __global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t 
         const size_t slot = (size_t)k * n + (size_t)i;
         StepResult r;
         if (live) {
-            r = v1_step<REGC>(L, s, P, env_id, actions != nullptr ? actions + slot * 2 * N : nullptr, C, con, form_base);
+            r = v1_step<REGC>(L, s, P, env_id, actions != nullptr ? actions + slot * 2 * N : nullptr, C, con, form_base,
+                              opp_actions != nullptr ? opp_actions + slot * 2 * N : nullptr);
             if (r.done && P.auto_reset) reset_env(L, s, P, env_id, form_base);
         } else {
             r.reward = 0.0; r.done = 0; r.flags = 0; r.contacts = 0; r.overflow = 0;
@@ -240,30 +244,30 @@ cudaError_t launch_reset(const V1Params &P, void *state, const uint8_t *mask, vo
     return cudaGetLastError();
 }
 
-cudaError_t launch_step(const V1Params &P, void *state, const uint8_t *actions, void *obs, void *reward, uint8_t *done,
-                        void *final_obs, int out_f64, cudaStream_t st)
+cudaError_t launch_step(const V1Params &P, void *state, const uint8_t *actions, const uint8_t *opp_actions, void *obs, void *reward,
+                        uint8_t *done, void *final_obs, int out_f64, cudaStream_t st)
 {
     const StateView v = make_view(state, P.n_envs, P.n_players);
     const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
     const int g = blocks_for(P.n_envs, t);
     const bool big = regc_for(P.n_players) == 2;
     if (out_f64) {
-        if (big) v1_step_kernel<double, 2><<<g, t, sm, st>>>(P, v, actions, (double *)obs, (double *)reward, done, (double *)final_obs);
-        else v1_step_kernel<double, 0><<<g, t, sm, st>>>(P, v, actions, (double *)obs, (double *)reward, done, (double *)final_obs);
+        if (big) v1_step_kernel<double, 2><<<g, t, sm, st>>>(P, v, actions, opp_actions, (double *)obs, (double *)reward, done, (double *)final_obs);
+        else v1_step_kernel<double, 0><<<g, t, sm, st>>>(P, v, actions, opp_actions, (double *)obs, (double *)reward, done, (double *)final_obs);
     } else {
-        if (big) v1_step_kernel<float, 2><<<g, t, sm, st>>>(P, v, actions, (float *)obs, (float *)reward, done, (float *)final_obs);
-        else v1_step_kernel<float, 0><<<g, t, sm, st>>>(P, v, actions, (float *)obs, (float *)reward, done, (float *)final_obs);
+        if (big) v1_step_kernel<float, 2><<<g, t, sm, st>>>(P, v, actions, opp_actions, (float *)obs, (float *)reward, done, (float *)final_obs);
+        else v1_step_kernel<float, 0><<<g, t, sm, st>>>(P, v, actions, opp_actions, (float *)obs, (float *)reward, done, (float *)final_obs);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_rollout(const V1Params &P, void *state, int K, const uint8_t *actions, float *obs, float *reward,
-                           uint8_t *done, FutbolStats *stats, cudaStream_t st)
+cudaError_t launch_rollout(const V1Params &P, void *state, int K, const uint8_t *actions, const uint8_t *opp_actions, float *obs,
+                           float *reward, uint8_t *done, FutbolStats *stats, cudaStream_t st)
 {
     const StateView v = make_view(state, P.n_envs, P.n_players);
     const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
-    if (regc_for(P.n_players) == 2) v1_rollout_kernel<2><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, K, actions, obs, reward, done, stats);
-    else v1_rollout_kernel<0><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, K, actions, obs, reward, done, stats);
+    if (regc_for(P.n_players) == 2) v1_rollout_kernel<2><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+    else v1_rollout_kernel<0><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
     return cudaGetLastError();
 }
 

@@ -479,10 +479,11 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
 struct StepResult { double reward; int done; int flags; int contacts; int overflow; };
 
 // Futbol.step, :427-483.  `left`: this env's 2N action bytes (arrow, key per left player) or nullptr =
-// synthetic uniform actions from Philox stream 1.
+// synthetic uniform actions from Philox stream 1.  `right`: the right team's 2N action bytes supplied by the caller (the
+// self-play hook) or nullptr = action_space.sample() (:429, Philox stream 2).
 template <int REGC>
 __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id, const uint8_t *left,
-                                              const PairCache &C, Contact *con, uint32_t form_base)
+                                              const PairCache &C, Contact *con, uint32_t form_base, const uint8_t *right = nullptr)
 {
     const int N = P.n_players, ball = 2 * N, bo = ball * kBodyStride;
     StepResult res;
@@ -510,6 +511,7 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
     for (int p = 0; p < 2 * N; ++p) {                                    // :447-453, right team = action_space.sample() (:429)
         int arrow, key;
         if (p < N && left != nullptr) { arrow = (int)((packed >> (6 * p)) & 7u); key = (int)((packed >> (6 * p + 3)) & 7u); }
+        else if (p >= N && right != nullptr) { arrow = right[2 * (p - N)] % 5; key = right[2 * (p - N) + 1] % 5; }
         else {
             const uint32_t stream = p < N ? kStreamActions : kStreamV1Opp;
             const int q = p < N ? p : p - N;

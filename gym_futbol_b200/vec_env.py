@@ -103,20 +103,23 @@ class FutbolVecEnv:
             _lib.check(self.lib.futbol_reset(self._h, _ptr(self.state), _ptr(m), _ptr(self.obs), self._dt, self._stream()))
         return self.obs
 
-    def step(self, actions):
-        """actions: [n] ints in 0..15 (ai_1 = a // 4, ai_2 = a % 4)."""
+    def step(self, actions, opp_actions=None):
+        """actions: [n] ints in 0..15 (ai_1 = a // 4, ai_2 = a % 4).  opp_actions: None = the reference's own opponents;
+        else the opponents' actions in the same format (self-play / learned opponents; v0 needs random_opp=True)."""
         with torch.cuda.device(self.device):
             a = self._actions(actions, (self.num_envs,) + self.act_shape)
-            _lib.check(self.lib.futbol_step(self._h, _ptr(self.state), _ptr(a), _ptr(self.obs), _ptr(self.rewards),
-                                            _ptr(self.dones), _ptr(self.final_obs), self._dt, self._stream()))
+            o = None if opp_actions is None else self._actions(opp_actions, (self.num_envs,) + self.act_shape)
+            _lib.check(self.lib.futbol_step_vs(self._h, _ptr(self.state), _ptr(a), _ptr(o), _ptr(self.obs), _ptr(self.rewards),
+                                               _ptr(self.dones), _ptr(self.final_obs), self._dt, self._stream()))
         return self.obs, self.rewards, self.dones, {"terminal_observation": self.final_obs}
 
-    def rollout(self, K, actions=None, obs=True, reward=True, done=True, out=None):
+    def rollout(self, K, actions=None, obs=True, reward=True, done=True, out=None, opp_actions=None):
         """K fused steps.  actions: uint8 [K, n] or None (uniform random actions drawn in-kernel).
 
         Returns (obs [K, n, 30] f32, reward [K, n] f32, done [K, n] u8).  By default the buffers are owned by
         this object and cached per K; ``out=(obs, reward, done)`` writes into caller-provided contiguous CUDA
         tensors of those shapes and dtypes instead (e.g. slices of a PPO rollout buffer); an entry may be None.
+        ``opp_actions``: uint8 [K, n(, 2N)] the opponents' actions supplied by the caller (open-loop self-play replay).
         """
         K = int(K)
         n = self.num_envs
@@ -136,8 +139,9 @@ class FutbolVecEnv:
             o, r, d = (o if obs else None), (r if reward else None), (d if done else None)
         with torch.cuda.device(self.device):
             a = None if actions is None else self._actions(actions, (K, n) + self.act_shape)
-            _lib.check(self.lib.futbol_rollout(self._h, _ptr(self.state), K, _ptr(a), _ptr(o), _ptr(r), _ptr(d),
-                                               _ptr(self.stats), self._stream()))
+            oa = None if opp_actions is None else self._actions(opp_actions, (K, n) + self.act_shape)
+            _lib.check(self.lib.futbol_rollout_vs(self._h, _ptr(self.state), K, _ptr(a), _ptr(oa), _ptr(o), _ptr(r), _ptr(d),
+                                                  _ptr(self.stats), self._stream()))
         return o, r, d
 
     # ------------------------------------------------------------------ state / statistics

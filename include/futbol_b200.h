@@ -125,6 +125,16 @@ int futbol_step(FutbolHandle *h, void *state, const uint8_t *actions, void *obs,
 int futbol_rollout(FutbolHandle *h, void *state, int K, const uint8_t *actions, float *obs,
                    float *reward, uint8_t *done, FutbolStats *stats, void *stream);
 
+/* ---- the same with the OPPONENTS' actions supplied by the caller (self-play / learned opponents) ----------
+ * Replaces the reference's opponent sources -- v0: `randint(0, 15)` (futbol_env.py:639-645; the handle must have
+ * been created with random_opp = 1, the draw is not taken); v1: `action_space.sample()` (envs_v1/futbol_env.py:429).
+ * opp_actions: v0 uint8[n] / [K, n] in 0..15 (opp_1 = a / 4, opp_2 = a % 4); v1 uint8[n, 2N] / [K, n, 2N] for the
+ * right team.  NULL = the reference's own opponents (then identical to futbol_step / futbol_rollout). */
+int futbol_step_vs(FutbolHandle *h, void *state, const uint8_t *actions, const uint8_t *opp_actions, void *obs,
+                   void *reward, uint8_t *done, void *final_obs, int out_dtype, void *stream);
+int futbol_rollout_vs(FutbolHandle *h, void *state, int K, const uint8_t *actions, const uint8_t *opp_actions,
+                      float *obs, float *reward, uint8_t *done, FutbolStats *stats, void *stream);
+
 /* ---- state access (device AoS records: FutbolV0EnvState / FutbolV1EnvState) ---------- */
 size_t futbol_env_state_bytes(const FutbolHandle *h); /* sizeof one AoS record */
 int futbol_get_state(FutbolHandle *h, const void *state, void *aos_out, void *stream);

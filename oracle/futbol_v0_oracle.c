@@ -621,7 +621,10 @@ static void opp_team_set_vector_observation(Ctx *c)
 }
 
 /* step, :628-717.  Returns done. */
-int futbol_v0_oracle_step(const OracleV0Config *cfg, OracleV0Env *e, int ai_action, double *reward_out)
+/* opp_action: -1 = the reference's own opponents (random draw :641 or the hard-coded team :649); 0..15 = actions
+ * supplied by the caller for opp_1 (a / 4) and opp_2 (a % 4) -- the self-play hook: they go through the same
+ * _agent_set_vector_observation path as the random opponents (:642-645) and the randint(0, 15) draw is not taken. */
+int futbol_v0_oracle_step_vs(const OracleV0Config *cfg, OracleV0Env *e, int ai_action, int opp_action, double *reward_out)
 {
     Ctx ctx = { cfg, e };
     Ctx *c = &ctx;
@@ -634,8 +637,8 @@ int futbol_v0_oracle_step(const OracleV0Config *cfg, OracleV0Env *e, int ai_acti
     e->step_draws = 0;
     e->normal_calls = 0;
 
-    if (cfg->random_opp) {                                  /* :639-645 */
-        int r = rng_randint(c, 0, 15);
+    if (opp_action >= 0 || cfg->random_opp) {               /* :639-645 */
+        int r = opp_action >= 0 ? (opp_action & 15) : rng_randint(c, 0, 15);
         agent_set_vector_observation(c, OPP_1, r / 4);
         agent_set_vector_observation(c, OPP_2, r % 4);
     } else {
@@ -673,6 +676,11 @@ int futbol_v0_oracle_step(const OracleV0Config *cfg, OracleV0Env *e, int ai_acti
 }
 
 /* ---- batch drivers (harness level, not part of the reference) ------------------------- */
+int futbol_v0_oracle_step(const OracleV0Config *cfg, OracleV0Env *e, int ai_action, double *reward_out)
+{
+    return futbol_v0_oracle_step_vs(cfg, e, ai_action, -1, reward_out);
+}
+
 /*
  * Steps n envs (global ids env_id0 .. env_id0+n-1) ``steps`` times.
  *   actions: [steps][n] uint8 or NULL (=> Philox action stream, index = env total step)
@@ -682,7 +690,7 @@ int futbol_v0_oracle_step(const OracleV0Config *cfg, OracleV0Env *e, int ai_acti
  */
 typedef struct {
     const OracleV0Config *cfg; OracleV0Env *envs; int n, steps, lo, hi, autoreset;
-    const uint8_t *actions;
+    const uint8_t *actions, *opp_actions;
     double *obs, *reward; uint8_t *done, *owner, *last_owner; int32_t *ai_score, *opp_score;
     uint64_t *draws; uint8_t *flags;
 } RolloutJob;
@@ -697,7 +705,7 @@ static void *rollout_worker(void *arg)
             size_t k = (size_t)t * n + i;
             int a = j->actions ? j->actions[k] : futbol_oracle_action(j->cfg->seed, e->env_id, e->t_total, 16);
             double r;
-            int d = futbol_v0_oracle_step(j->cfg, e, a, &r);
+            int d = futbol_v0_oracle_step_vs(j->cfg, e, a, j->opp_actions ? j->opp_actions[k] : -1, &r);
             int fl = e->flags;
             if (j->obs && (j->autoreset != 2 || !d)) memcpy(j->obs + k * 30, e->obs, sizeof(double) * 30);
             if (j->reward) j->reward[k] = r;
@@ -717,8 +725,8 @@ static void *rollout_worker(void *arg)
     return NULL;
 }
 
-void futbol_v0_oracle_rollout(const OracleV0Config *cfg, OracleV0Env *envs, int n, int steps,
-                              const uint8_t *actions, int autoreset, int n_threads,
+void futbol_v0_oracle_rollout_vs(const OracleV0Config *cfg, OracleV0Env *envs, int n, int steps,
+                              const uint8_t *actions, const uint8_t *opp_actions, int autoreset, int n_threads,
                               double *obs, double *reward, uint8_t *done, uint8_t *owner,
                               uint8_t *last_owner, int32_t *ai_score, int32_t *opp_score,
                               uint64_t *draws, uint8_t *flags)
@@ -730,12 +738,22 @@ void futbol_v0_oracle_rollout(const OracleV0Config *cfg, OracleV0Env *envs, int 
     pthread_t th[256];
     for (int w = 0; w < n_threads; ++w) {
         RolloutJob j = { cfg, envs, n, steps, (int)((long)n * w / n_threads), (int)((long)n * (w + 1) / n_threads),
-                         autoreset, actions, obs, reward, done, owner, last_owner, ai_score, opp_score, draws, flags };
+                         autoreset, actions, opp_actions, obs, reward, done, owner, last_owner, ai_score, opp_score, draws, flags };
         jobs[w] = j;
     }
     if (n_threads == 1) { rollout_worker(&jobs[0]); return; }
     for (int w = 0; w < n_threads; ++w) pthread_create(&th[w], NULL, rollout_worker, &jobs[w]);
     for (int w = 0; w < n_threads; ++w) pthread_join(th[w], NULL);
+}
+
+void futbol_v0_oracle_rollout(const OracleV0Config *cfg, OracleV0Env *envs, int n, int steps,
+                              const uint8_t *actions, int autoreset, int n_threads,
+                              double *obs, double *reward, uint8_t *done, uint8_t *owner,
+                              uint8_t *last_owner, int32_t *ai_score, int32_t *opp_score,
+                              uint64_t *draws, uint8_t *flags)
+{
+    futbol_v0_oracle_rollout_vs(cfg, envs, n, steps, actions, NULL, autoreset, n_threads, obs, reward, done, owner, last_owner,
+                                ai_score, opp_score, draws, flags);
 }
 
 size_t futbol_v0_oracle_env_bytes(void) { return sizeof(OracleV0Env); }

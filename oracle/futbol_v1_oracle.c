@@ -409,11 +409,15 @@ static void space_step(const OracleV1Config *c, OracleV1Env *e)
 }
 
 /* ---- Futbol.step, :427-483 ------------------------------------------------------------------------ */
-int futbol_v1_oracle_step(const OracleV1Config *c, OracleV1Env *e, const uint8_t *left_actions, double *reward_out)
+/* right_actions: NULL = action_space.sample() (:429, Philox stream 2); else 2N bytes supplied by the caller for the
+ * right team (the self-play hook). */
+int futbol_v1_oracle_step_vs(const OracleV1Config *c, OracleV1Env *e, const uint8_t *left_actions, const uint8_t *right_actions,
+                             double *reward_out)
 {
     const int N = c->n_players, ball = 2 * N;
     uint8_t right[2 * V1_MAX_N];
-    futbol_v1_oracle_team_actions(c->seed, e->env_id, 2, e->t_total, N, right);   /* :429 */
+    if (right_actions) memcpy(right, right_actions, (size_t)(2 * N));
+    else futbol_v1_oracle_team_actions(c->seed, e->env_id, 2, e->t_total, N, right);   /* :429 */
     e->step_draws = 0;
     e->flags = 0;
     double init_d[V1_MAX_N];                                      /* :433 */
@@ -475,11 +479,16 @@ int futbol_v1_oracle_step(const OracleV1Config *c, OracleV1Env *e, const uint8_t
     return done;
 }
 
+int futbol_v1_oracle_step(const OracleV1Config *c, OracleV1Env *e, const uint8_t *left_actions, double *reward_out)
+{
+    return futbol_v1_oracle_step_vs(c, e, left_actions, NULL, reward_out);
+}
+
 /* ---- batched rollout (threads over envs) -------------------------------------------------------------
  * actions: NULL = synthetic left actions from stream 1, else uint8 [steps][n][2N].
  * autoreset: 0 none; 2 VecEnv semantics (reset in the same step, obs slot holds the reset observation). */
 typedef struct {
-    const OracleV1Config *cfg; OracleV1Env *envs; int n, steps, lo, hi, autoreset; const uint8_t *actions;
+    const OracleV1Config *cfg; OracleV1Env *envs; int n, steps, lo, hi, autoreset; const uint8_t *actions, *right_actions;
     double *obs, *reward; uint8_t *done, *flags;
 } Job;
 
@@ -496,7 +505,7 @@ static void *job_main(void *arg)
             if (j->actions) act = j->actions + slot * 2 * N;
             else { futbol_v1_oracle_team_actions(j->cfg->seed, e->env_id, 1, e->t_total, N, synth); act = synth; }
             double r;
-            int d = futbol_v1_oracle_step(j->cfg, e, act, &r);
+            int d = futbol_v1_oracle_step_vs(j->cfg, e, act, j->right_actions ? j->right_actions + slot * 2 * N : NULL, &r);
             int fl = e->flags;
             if (d && j->autoreset) futbol_v1_oracle_reset(j->cfg, e);
             if (j->obs) futbol_v1_oracle_obs(j->cfg, e, j->obs + slot * D);
@@ -508,8 +517,9 @@ static void *job_main(void *arg)
     return NULL;
 }
 
-void futbol_v1_oracle_rollout(const OracleV1Config *cfg, OracleV1Env *envs, int n, int steps, const uint8_t *actions,
-                              int autoreset, int n_threads, double *obs, double *reward, uint8_t *done, uint8_t *flags)
+void futbol_v1_oracle_rollout_vs(const OracleV1Config *cfg, OracleV1Env *envs, int n, int steps, const uint8_t *actions,
+                                 const uint8_t *right_actions, int autoreset, int n_threads, double *obs, double *reward,
+                                 uint8_t *done, uint8_t *flags)
 {
     if (n_threads < 1) n_threads = 1;
     if (n_threads > n) n_threads = n;
@@ -518,8 +528,14 @@ void futbol_v1_oracle_rollout(const OracleV1Config *cfg, OracleV1Env *envs, int 
     if (n_threads > 256) n_threads = 256;
     for (int t = 0; t < n_threads; ++t) {
         jobs[t] = (Job){ cfg, envs, n, steps, (int)((long long)n * t / n_threads), (int)((long long)n * (t + 1) / n_threads),
-                         autoreset, actions, obs, reward, done, flags };
+                         autoreset, actions, right_actions, obs, reward, done, flags };
         if (n_threads == 1) job_main(&jobs[t]); else pthread_create(&th[t], NULL, job_main, &jobs[t]);
     }
     if (n_threads > 1) for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+}
+
+void futbol_v1_oracle_rollout(const OracleV1Config *cfg, OracleV1Env *envs, int n, int steps, const uint8_t *actions,
+                              int autoreset, int n_threads, double *obs, double *reward, uint8_t *done, uint8_t *flags)
+{
+    futbol_v1_oracle_rollout_vs(cfg, envs, n, steps, actions, NULL, autoreset, n_threads, obs, reward, done, flags);
 }

@@ -54,6 +54,9 @@ def lib():
         assert _lib.futbol_v0_oracle_cfg_bytes() == C.sizeof(OracleV0Config)
         _lib.futbol_v0_oracle_step.restype = C.c_int
         _lib.futbol_v0_oracle_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        _lib.futbol_v0_oracle_rollout_vs.restype = None
+        _lib.futbol_v0_oracle_rollout_vs.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                                     C.c_int] + [C.c_void_p] * 9
         _lib.futbol_v0_oracle_rollout.restype = None
         _lib.futbol_v0_oracle_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                                   C.c_int] + [C.c_void_p] * 9
@@ -90,7 +93,7 @@ class OracleV0:
                                            int(action), C.byref(r))
         return self.envs["obs"][i].copy(), r.value, bool(d)
 
-    def rollout(self, steps, actions=None, autoreset=1, n_threads=1, record=True):
+    def rollout(self, steps, actions=None, autoreset=1, n_threads=1, record=True, opp_actions=None):
         n = self.n
         out = {}
         if record:
@@ -101,8 +104,10 @@ class OracleV0:
                    "flags": np.zeros((steps, n), np.uint8)}
         if actions is not None:
             actions = np.ascontiguousarray(actions, dtype=np.uint8).reshape(steps, n)
+        if opp_actions is not None:
+            opp_actions = np.ascontiguousarray(opp_actions, dtype=np.uint8).reshape(steps, n)
         g = out.get
-        self.lib.futbol_v0_oracle_rollout(C.byref(self.cfg), _ptr(self.envs), n, int(steps), _ptr(actions),
+        self.lib.futbol_v0_oracle_rollout_vs(C.byref(self.cfg), _ptr(self.envs), n, int(steps), _ptr(actions), _ptr(opp_actions),
                                           int(autoreset), int(n_threads), _ptr(g("obs")), _ptr(g("reward")),
                                           _ptr(g("done")), _ptr(g("owner")), _ptr(g("last_owner")),
                                           _ptr(g("ai_score")), _ptr(g("opp_score")), _ptr(g("draws")),

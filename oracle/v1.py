@@ -42,6 +42,7 @@ def lib():
         L.futbol_v1_oracle_step.restype = C.c_int
         L.futbol_v1_oracle_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         L.futbol_v1_oracle_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
+        L.futbol_v1_oracle_rollout_vs.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
         L.futbol_v1_oracle_team_actions.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -80,7 +81,7 @@ class OracleV1:
         d = self.lib.futbol_v1_oracle_step(_ptr(self.cfg), C.c_void_p(self.envs[i:i + 1].ctypes.data), _ptr(a), C.byref(r))
         return self.obs(i), r.value, bool(d)
 
-    def rollout(self, steps, actions=None, autoreset=2, n_threads=1, record=True):
+    def rollout(self, steps, actions=None, autoreset=2, n_threads=1, record=True, right_actions=None):
         n, D = self.n, self.obs_dim
         out = {}
         if record:
@@ -88,8 +89,10 @@ class OracleV1:
                    "flags": np.zeros((steps, n), np.uint8)}
         if actions is not None:
             actions = np.ascontiguousarray(actions, dtype=np.uint8).reshape(steps, n, 2 * self.N)
+        if right_actions is not None:
+            right_actions = np.ascontiguousarray(right_actions, dtype=np.uint8).reshape(steps, n, 2 * self.N)
         g = out.get
-        self.lib.futbol_v1_oracle_rollout(_ptr(self.cfg), _ptr(self.envs), n, int(steps), _ptr(actions), int(autoreset),
+        self.lib.futbol_v1_oracle_rollout_vs(_ptr(self.cfg), _ptr(self.envs), n, int(steps), _ptr(actions), _ptr(right_actions), int(autoreset),
                                           int(n_threads), _ptr(g("obs")), _ptr(g("reward")), _ptr(g("done")), _ptr(g("flags")))
         return out
 
