@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--minibatches", type=int, default=4)
     ap.add_argument("--epochs", type=int, default=4)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--bf16", type=int, default=1, help="run the torch policy under bf16 autocast (the simulator is fp64 either way)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(args.seed)
@@ -56,7 +57,8 @@ def main():
     n, T = args.envs, args.steps
     env = FutbolVecEnv(n, device=dev, seed=args.seed, random_opp=False)
     policy = Policy().to(dev)
-    opt = torch.optim.Adam(policy.parameters(), lr=2.5e-4, eps=1e-5)
+    opt = torch.optim.Adam(policy.parameters(), lr=2.5e-4, eps=1e-5, fused=True)
+    amp = lambda: torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(args.bf16))  # noqa: E731
     obs_buf = torch.empty((T, n, 30), device=dev)
     act_buf = torch.empty((T, n), dtype=torch.uint8, device=dev)
     logp_buf = torch.empty((T, n), device=dev)
@@ -71,16 +73,19 @@ def main():
         with torch.no_grad():
             for t in range(T):
                 obs_buf[t].copy_(obs)
-                logits, val_buf[t] = policy(obs)
-                dist = torch.distributions.Categorical(logits=logits)
-                a = dist.sample()
+                with amp():
+                    logits, v = policy(obs)
+                val_buf[t] = v.float()
+                logp_all = torch.log_softmax(logits.float(), dim=-1)
+                a = torch.multinomial(logp_all.exp(), 1).squeeze(-1)
                 act_buf[t] = a.to(torch.uint8)
-                logp_buf[t] = dist.log_prob(a)
+                logp_buf[t] = logp_all.gather(1, a.unsqueeze(1)).squeeze(1)
                 obs, rew, done, _ = env.step(act_buf[t])
                 assert obs.data_ptr() == env.obs.data_ptr()
                 rew_buf[t].copy_(rew)
                 done_buf[t].copy_(done)
-            val_buf[T] = policy(obs)[1]
+            with amp():
+                val_buf[T] = policy(obs)[1].float()
             adv, ret = gae(rew_buf, done_buf, val_buf, 0.99, 0.95)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
@@ -91,7 +96,9 @@ def main():
             perm = torch.randperm(T * n, device=dev)
             for k in range(args.minibatches):
                 idx = perm[k * mb:(k + 1) * mb]
-                logits, v = policy(b_obs[idx])
+                with amp():
+                    logits, v = policy(b_obs[idx])
+                logits, v = logits.float(), v.float()
                 dist = torch.distributions.Categorical(logits=logits)
                 logp = dist.log_prob(b_act[idx])
                 a_ = b_adv[idx]
