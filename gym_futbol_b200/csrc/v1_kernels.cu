@@ -215,11 +215,11 @@ __global__ void v1_get_state_kernel(int n, int n_players, StateView v, FutbolV1E
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int B = 2 * n_players + 1;
-    FutbolV1EnvState e;
-    for (int b = 0; b < 21; ++b) for (int f = 0; f < 6; ++f) e.body[b][f] = b < B ? v.body[(size_t)(6 * b + f) * v.np + i] : 0.0;
-    e.t_total = v.t_total[i]; e.stamp = v.stamp[i]; e.ep_step = v.ep_step[i]; e.owner_side = v.owner_side[i];
-    e.flags = v.flags[i]; e.pad_[0] = e.pad_[1] = 0;
-    out[i] = e;
+    FutbolV1EnvState *e = out + i;                    // written field by field: the record is 1 KB
+    for (int b = 0; b < 21; ++b)
+        for (int f = 0; f < 6; ++f) e->body[b][f] = b < B ? v.body[(size_t)(6 * b + f) * v.np + i] : 0.0;
+    e->t_total = v.t_total[i]; e->stamp = v.stamp[i]; e->ep_step = v.ep_step[i]; e->owner_side = v.owner_side[i];
+    e->flags = v.flags[i]; e->pad_[0] = e->pad_[1] = 0;
 }
 
 // ---- host launchers ------------------------------------------------------------------------------------
