@@ -119,33 +119,53 @@ __global__ void __launch_bounds__(kEnvThreads) v0_reset_kernel(V0Params P, State
     if (obs != nullptr) thread_store_obs(obs + (size_t)i * kObsDim, L, s);
 }
 
+#ifndef FUTBOL_MIN_BLOCKS
+#define FUTBOL_MIN_BLOCKS 5     // resident blocks per SM the register allocation is sized for (shared memory allows 5)
+#endif
+
 // ---- per-step API ----------------------------------------------------------------------------------
 template <typename T, bool RANDOM_OPP>
-__global__ void __launch_bounds__(kEnvThreads) v0_step_kernel(V0Params P, StateView v, const uint8_t *actions,
+__global__ void __launch_bounds__(kEnvThreads, FUTBOL_MIN_BLOCKS) v0_step_kernel(V0Params P, StateView v, const uint8_t *actions,
                                                               const uint8_t *opp_actions, T *obs, T *reward, uint8_t *done,
                                                               T *final_obs)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_envs) return;
-    const Lane L = make_lane(threadIdx.x >> 5, threadIdx.x & 31);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_env0 = i - lane;
+    if (warp_env0 >= P.n_envs) return;            // whole warp out of range
+    const bool live = i < P.n_envs;
+    const int rows_in_warp = min(32, P.n_envs - warp_env0);
+    const Lane L = make_lane(warp, lane);
     V0Regs s;
-    load_state(v, i, L, s);
-    const StepResult r = v0_step<RANDOM_OPP>(L, s, P, P.env_id_offset + (uint32_t)i, actions[i] & 15,
-                                             opp_actions != nullptr ? (int)(opp_actions[i] & 15) : -1);
-    if (r.done && P.auto_reset) {
-        if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * kObsDim, L, s);
-        reset_env(L, s);
+    StepResult r;
+    r.reward = 0.0; r.done = 0; r.flags = 0;
+    if (live) {
+        load_state(v, i, L, s);
+        r = v0_step<RANDOM_OPP>(L, s, P, P.env_id_offset + (uint32_t)i, actions[i] & 15,
+                                opp_actions != nullptr ? (int)(opp_actions[i] & 15) : -1);
+        if (r.done && P.auto_reset) {
+            if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * kObsDim, L, s);
+            reset_env(L, s);
+        }
+        store_state(v, i, L, s, r.flags);
+        if (reward != nullptr) reward[i] = (T)r.reward;
+        if (done != nullptr) done[i] = (uint8_t)r.done;
+    } else {
+        s.t_total = 0; reset_env(L, s);           // padding lanes of the last warp: a private dummy env for the staged store
     }
-    store_state(v, i, L, s, r.flags);
-    if (obs != nullptr) thread_store_obs(obs + (size_t)i * kObsDim, L, s);
-    if (reward != nullptr) reward[i] = (T)r.reward;
-    if (done != nullptr) done[i] = (uint8_t)r.done;
+    if (obs != nullptr) {
+        if (sizeof(T) == 4) {                     // fp32: staged through shared memory, 128-bit coalesced stores
+            float *stage = reinterpret_cast<float *>(futbol_smem + warp * kWarpSmemBytes + kWarpStateBytes);
+            float *dst = reinterpret_cast<float *>(obs) + (size_t)warp_env0 * kObsDim;
+            const bool vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+            warp_store_obs_f32(L, s, stage, dst, lane, rows_in_warp, vec_ok);
+        } else if (live) {
+            thread_store_obs(obs + (size_t)i * kObsDim, L, s);
+        }
+    }
 }
 
 // ---- fused K-step rollout ----------------------------------------------------------------------------
-#ifndef FUTBOL_MIN_BLOCKS
-#define FUTBOL_MIN_BLOCKS 5     // resident blocks per SM the register allocation is sized for (shared memory allows 5)
-#endif
 
 template <bool RANDOM_OPP>
 __global__ void __launch_bounds__(kEnvThreads, FUTBOL_MIN_BLOCKS)
