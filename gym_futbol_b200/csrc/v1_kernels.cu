@@ -111,24 +111,33 @@ __global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, 
     const uint32_t form_base = stage_formation(P, blockDim.x >> 5, threadIdx.x, blockDim.x);
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_envs) return;
+    const int lane = threadIdx.x & 31;
+    const int warp_env0 = i - lane;
+    if (warp_env0 >= P.n_envs) return;
+    const bool live = i < P.n_envs;
+    const int rows_in_warp = min(32, P.n_envs - warp_env0);
     const int N = P.n_players, B = 2 * N + 1, D = obs_dim(N);
-    const Lane L = make_lane(threadIdx.x >> 5, threadIdx.x & 31, N);
+    const Lane L = make_lane(threadIdx.x >> 5, lane, N);
     const uint32_t env_id = P.env_id_offset + (uint32_t)i;
-    const PairCache C{v.jn + i, v.last + i, v.np};
-    Contact con[kMaxContacts];
     V1Regs s;
-    load_state(v, i, L, s, B);
-    const StepResult r = v1_step<REGC>(L, s, P, env_id, actions + (size_t)i * 2 * N, C, con, form_base,
-                                       opp_actions != nullptr ? opp_actions + (size_t)i * 2 * N : nullptr);
-    if (r.done && P.auto_reset) {
-        if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * D, L, N);
-        reset_env(L, s, P, env_id, form_base);
+    if (live) {
+        const PairCache C{v.jn + i, v.last + i, v.np};
+        Contact con[kMaxContacts];
+        load_state(v, i, L, s, B);
+        const StepResult r = v1_step<REGC>(L, s, P, env_id, actions + (size_t)i * 2 * N, C, con, form_base,
+                                           opp_actions != nullptr ? opp_actions + (size_t)i * 2 * N : nullptr);
+        if (r.done && P.auto_reset) {
+            if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * D, L, N);
+            reset_env(L, s, P, env_id, form_base);
+        }
+        store_state(v, i, L, s, B, r.flags);
+        if (reward != nullptr) reward[i] = (T)r.reward;
+        if (done != nullptr) done[i] = (uint8_t)r.done;
     }
-    store_state(v, i, L, s, B, r.flags);
-    if (obs != nullptr) thread_store_obs(obs + (size_t)i * D, L, N);
-    if (reward != nullptr) reward[i] = (T)r.reward;
-    if (done != nullptr) done[i] = (uint8_t)r.done;
+    if (obs != nullptr) {
+        if (sizeof(T) == 4) warp_store_obs_f32(L, N, reinterpret_cast<float *>(obs) + (size_t)warp_env0 * D, lane, rows_in_warp);
+        else if (live) thread_store_obs(obs + (size_t)i * D, L, N);
+    }
 }
 
 template <int REGC>

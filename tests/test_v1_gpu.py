@@ -132,3 +132,30 @@ def test_v1_masked_reset_matches_oracle(torch_cuda):
         assert np.array_equal(obs.cpu().numpy(), want["obs"][t]) and np.array_equal(rew.cpu().numpy(), want["reward"][t])
     st = env.get_state()
     assert (st["ep_step"][mask == 1] == 60).all() and (st["ep_step"][mask == 0] == 120).all()
+
+
+def test_v1_and_v0_step_api_float32_outputs_ragged_batch(torch_cuda):
+    """fp32 per-step outputs take the warp-cooperative observation writer; 77 envs leave a partial last warp."""
+    from gym_futbol_b200 import FutbolV1VecEnv, FutbolVecEnv
+    from oracle import philox
+    from oracle.v0 import OracleV0
+    from oracle.v1 import OracleV1
+    n, steps = 77, 60
+    env = FutbolV1VecEnv(n, number_of_player=2, seed=3)
+    orc = OracleV1(n, seed=3, number_of_player=2)
+    env.reset()
+    acts = np.random.default_rng(5).integers(0, 5, (steps, n, 4), dtype=np.uint8)
+    want = orc.rollout(steps, actions=acts, autoreset=2)
+    for t in range(steps):
+        obs, rew, done, _ = env.step(torch_cuda.from_numpy(acts[t]).cuda())
+        assert obs.dtype == torch_cuda.float32 and np.array_equal(obs.cpu().numpy(), want["obs"][t].astype(np.float32))
+        assert np.array_equal(rew.cpu().numpy(), want["reward"][t].astype(np.float32))
+    env0 = FutbolVecEnv(n, seed=3, random_opp=False)
+    orc0 = OracleV0(n, seed=3, random_opp=False, arith=0)
+    env0.reset()
+    a0 = philox.actions_table(3, np.arange(n), 0, steps)
+    want0 = orc0.rollout(steps, actions=a0, autoreset=2)
+    for t in range(steps):
+        obs, rew, done, _ = env0.step(torch_cuda.from_numpy(a0[t]).cuda())
+        assert np.array_equal(obs.cpu().numpy(), want0["obs"][t].astype(np.float32))
+        assert np.array_equal(rew.cpu().numpy(), want0["reward"][t].astype(np.float32)) and np.array_equal(done.cpu().numpy(), want0["done"][t])
