@@ -234,7 +234,7 @@ __global__ void v1_get_state_kernel(int n, int n_players, StateView v, FutbolV1E
 // ---- host launchers ------------------------------------------------------------------------------------
 static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 static inline int threads_for(int n_players) { return n_players <= 5 ? 64 : 32; }   // keeps a block under 48 KB of shared memory (10v10: 33 KB per warp)
-static inline int regc_for(int n_players) { return n_players >= 4 ? 2 : 0; }   // contacts kept in registers by the solver (v1_step.cuh space_step)
+static inline int regc_for(int n_players) { return n_players >= 4 ? 2 : (n_players >= 2 ? 1 : 0); }   // contacts kept in registers by the solver (v1_step.cuh space_step)
 static inline int smem_for(int n_players) { return block_smem_bytes(n_players, threads_for(n_players) / 32); }
 
 cudaError_t launch_reset(const V1Params &P, void *state, const uint8_t *mask, void *obs, int obs_f64, int init, cudaStream_t st)
@@ -258,15 +258,11 @@ cudaError_t launch_step(const V1Params &P, void *state, const uint8_t *actions, 
 {
     const StateView v = make_view(state, P.n_envs, P.n_players);
     const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
-    const int g = blocks_for(P.n_envs, t);
-    const bool big = regc_for(P.n_players) == 2;
-    if (out_f64) {
-        if (big) v1_step_kernel<double, 2><<<g, t, sm, st>>>(P, v, actions, opp_actions, (double *)obs, (double *)reward, done, (double *)final_obs);
-        else v1_step_kernel<double, 0><<<g, t, sm, st>>>(P, v, actions, opp_actions, (double *)obs, (double *)reward, done, (double *)final_obs);
-    } else {
-        if (big) v1_step_kernel<float, 2><<<g, t, sm, st>>>(P, v, actions, opp_actions, (float *)obs, (float *)reward, done, (float *)final_obs);
-        else v1_step_kernel<float, 0><<<g, t, sm, st>>>(P, v, actions, opp_actions, (float *)obs, (float *)reward, done, (float *)final_obs);
-    }
+    const int g = blocks_for(P.n_envs, t), rc = regc_for(P.n_players);
+#define FUTBOL_V1_STEP(T, RC) v1_step_kernel<T, RC><<<g, t, sm, st>>>(P, v, actions, opp_actions, (T *)obs, (T *)reward, done, (T *)final_obs)
+    if (out_f64) { if (rc == 2) FUTBOL_V1_STEP(double, 2); else if (rc == 1) FUTBOL_V1_STEP(double, 1); else FUTBOL_V1_STEP(double, 0); }
+    else { if (rc == 2) FUTBOL_V1_STEP(float, 2); else if (rc == 1) FUTBOL_V1_STEP(float, 1); else FUTBOL_V1_STEP(float, 0); }
+#undef FUTBOL_V1_STEP
     return cudaGetLastError();
 }
 
@@ -275,8 +271,10 @@ cudaError_t launch_rollout(const V1Params &P, void *state, int K, const uint8_t 
 {
     const StateView v = make_view(state, P.n_envs, P.n_players);
     const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
-    if (regc_for(P.n_players) == 2) v1_rollout_kernel<2><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
-    else v1_rollout_kernel<0><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+    const int g = blocks_for(P.n_envs, t), rc = regc_for(P.n_players);
+    if (rc == 2) v1_rollout_kernel<2><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+    else if (rc == 1) v1_rollout_kernel<1><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+    else v1_rollout_kernel<0><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
     return cudaGetLastError();
 }
 

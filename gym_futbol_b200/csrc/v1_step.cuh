@@ -355,8 +355,8 @@ __device__ __forceinline__ void warm_start_contact(Lane L, const Contact &k, int
 // The first two contacts of a step live in registers (c0, c1), the rest in the local-memory list `con` (index
 // i - 2): a step rarely has more than two, and the ten solver iterations would otherwise wait on local-memory
 // loads (L1 is small next to 200 KB of shared memory: ncu showed 53 % of the long-scoreboard stalls there).
-// REGC = how many contacts are register-resident: 2 for the larger teams, 0 for N <= 3 where contacts are rare and
-// the extra registers cost more occupancy than the loads cost time (measured: 2v2 -20 % with REGC = 2).
+// REGC = how many contacts are register-resident, chosen by measurement: 2 for N >= 4, 1 for N = 2, 3 (a second
+// one costs more occupancy than its loads cost time: 2v2 -20 %), 0 for 1v1 (-14 % with one).
 template <int REGC>
 __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, const PairCache &C, Contact *con, int &overflow)
 {

@@ -52,6 +52,7 @@ void host_v1_rollout(uint64_t seed, uint32_t env_id0, int n_players, int ep_limi
         for (int k = 0; k < steps; ++k) {
             const size_t slot = (size_t)k * n + i;
             const StepResult r = (N >= 4) ? v1_step<2>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con, form_base)
+                                 : (N >= 2) ? v1_step<1>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con, form_base)
                                           : v1_step<0>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con, form_base);
             if (r.done) reset_env(L, s, P, env_id, form_base);
             if (obs) for (int e = 0; e < D; ++e) obs[slot * D + e] = obs_elem(L, N, e);
