@@ -1,0 +1,53 @@
+"""Large-scale bit-exactness soak: tens of thousands of environments for thousands of steps, final states compared
+with the oracle (no per-step recording on the CPU side).  Catches what small cases cannot: rare draw counts, rare
+branches (kicks from the touchline, simultaneous intercepts), and any operand outside the guard-free arithmetic's
+domain would show up here as a mismatch."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("random_opp", [False, True])
+def test_v0_soak_final_state_bit_exact(random_opp):
+    import torch
+    from gym_futbol_b200 import FutbolVecEnv
+    from oracle.v0 import OracleV0
+    n, K, reps, seed, off = 32768, 250, 8, 77, 123456
+    env = FutbolVecEnv(n, seed=seed, env_id_offset=off, random_opp=random_opp)
+    env.reset()
+    orc = OracleV0(n, seed=seed, env_id0=off, random_opp=random_opp, arith=0)
+    for _ in range(reps):                               # 2000 steps: five 401-step episodes per env
+        env.rollout(K, obs=False, reward=False, done=False)
+        orc.rollout(K, actions=None, autoreset=2, n_threads=16, record=False)
+    torch.cuda.synchronize()
+    st = env.get_state()
+    e = orc.envs
+    assert np.array_equal(st["rows"].reshape(n, 25), e["obs"][:, :5].reshape(n, 25))
+    assert np.array_equal(st["owner"], e["owner"].astype(np.uint8)) and np.array_equal(st["last_owner"], e["last_owner"].astype(np.uint8))
+    assert np.array_equal(st["ai_score"], e["ai_score"]) and np.array_equal(st["opp_score"], e["opp_score"])
+    assert np.array_equal(st["t_total"], e["t_total"]) and (st["t_total"] == K * reps).all()
+    stats = env.read_stats()
+    assert stats["env_steps"] == n * K * reps and stats["episodes"] == n * (K * reps // 401)
+
+
+@pytest.mark.parametrize("N,n", [(2, 16384), (5, 4096)])
+def test_v1_soak_final_state_bit_exact(N, n):
+    import torch
+    from gym_futbol_b200 import FutbolV1VecEnv
+    from oracle.v1 import OracleV1
+    K, reps, seed, off = 250, 6, 31, 5000
+    env = FutbolV1VecEnv(n, number_of_player=N, seed=seed, env_id_offset=off)
+    env.reset()
+    orc = OracleV1(n, seed=seed, env_id0=off, number_of_player=N)
+    for _ in range(reps):                               # 1500 steps: five 300-step episodes per env
+        env.rollout(K, obs=False, reward=False, done=False)
+        orc.rollout(K, actions=None, autoreset=2, n_threads=16, record=False)
+    torch.cuda.synchronize()
+    st = env.get_state()
+    B = 2 * N + 1
+    assert np.array_equal(st["body"][:, :B, 0:2], orc.envs["p"][:, :B]) and np.array_equal(st["body"][:, :B, 2:4], orc.envs["v"][:, :B])
+    assert np.array_equal(st["body"][:, :B, 4:6], orc.envs["vb"][:, :B])
+    assert np.array_equal(st["owner_side"], orc.envs["owner_side"].astype(np.uint8)) and np.array_equal(st["ep_step"], orc.envs["ep_step"])
+    stats = env.read_stats()
+    assert stats["contacts_dropped"] == 0 and orc.envs["overflow"].sum() == 0 and stats["episodes"] == n * (K * reps // 300)
