@@ -43,7 +43,8 @@ STATS_DTYPE = np.dtype([("reward_sum", np.float64), ("env_steps", np.uint64), ("
 EXPORTS = ("futbol_create", "futbol_destroy", "futbol_last_error", "futbol_abi_version", "futbol_state_bytes",
            "futbol_obs_dim", "futbol_act_dim", "futbol_draw_limit_steps", "futbol_reset", "futbol_step",
            "futbol_rollout", "futbol_env_state_bytes", "futbol_get_state", "futbol_set_state",
-           "futbol_launch_count", "futbol_gae", "futbol_selftest_arith", "futbol_step_vs", "futbol_rollout_vs")
+           "futbol_launch_count", "futbol_gae", "futbol_selftest_arith", "futbol_step_vs", "futbol_rollout_vs",
+           "futbol_set_rollout_slices")
 
 _lib = None
 
@@ -88,6 +89,8 @@ def load():
     for name in ("futbol_obs_dim", "futbol_act_dim", "futbol_draw_limit_steps"):
         getattr(L, name).restype = C.c_int
         getattr(L, name).argtypes = [vp]
+    L.futbol_set_rollout_slices.restype = C.c_int
+    L.futbol_set_rollout_slices.argtypes = [vp, C.c_int]
     L.futbol_launch_count.restype = C.c_uint64
     L.futbol_launch_count.argtypes = [vp]
     L.futbol_reset.restype = C.c_int

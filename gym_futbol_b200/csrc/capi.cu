@@ -24,6 +24,7 @@ struct FutbolHandle {
     bool is_v1;
     uint64_t launches;
     bool initialised;   // first futbol_reset zeroes t_total
+    int rollout_slices; // 0 = chosen per launch from the batch size (v0_kernels.cu)
 };
 
 static thread_local char g_err[256] = "";
@@ -116,6 +117,7 @@ int futbol_create(const FutbolConfig *cfg, FutbolHandle **out)
     h->cfg = *cfg;
     h->launches = 0;
     h->initialised = false;
+    h->rollout_slices = 0;
     h->is_v1 = is_v1;
     if (is_v1) {
         v1::V1Params &Q = h->v1;
@@ -166,6 +168,13 @@ int futbol_act_dim(const FutbolHandle *h) { return h ? (h->is_v1 ? 2 * h->cfg.n_
 int futbol_draw_limit_steps(const FutbolHandle *h) { return h ? (h->is_v1 ? h->v1.ep_limit : h->v0.ep_limit + 1) : 0; }
 uint64_t futbol_launch_count(const FutbolHandle *h) { return h ? h->launches : 0; }
 
+int futbol_set_rollout_slices(FutbolHandle *h, int slices)
+{
+    if (h == nullptr || slices < 0) return fail(FUTBOL_ERR_ARG, "null handle or negative slice count%s");
+    h->rollout_slices = slices;
+    return FUTBOL_OK;
+}
+
 int futbol_reset(FutbolHandle *h, void *state, const uint8_t *mask, void *obs, int obs_dtype, void *stream)
 {
     if (h == nullptr || state == nullptr) return fail(FUTBOL_ERR_ARG, "null handle/state%s");
@@ -210,7 +219,7 @@ int futbol_rollout_vs(FutbolHandle *h, void *state, int K, const uint8_t *action
     if (K <= 0) return fail(FUTBOL_ERR_ARG, "K must be positive%s");
     if (!h->initialised) return fail(FUTBOL_ERR_ARG, "futbol_reset must be called before futbol_rollout%s");
     cudaError_t e = h->is_v1 ? v1::launch_rollout(h->v1, state, K, actions, opp_actions, obs, reward, done, stats, (cudaStream_t)stream)
-                             : v0_launch_rollout(h->v0, state, K, actions, opp_actions, obs, reward, done, stats, (cudaStream_t)stream);
+                             : v0_launch_rollout(h->v0, state, K, actions, opp_actions, obs, reward, done, stats, h->rollout_slices, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     h->launches += 1;
     return FUTBOL_OK;

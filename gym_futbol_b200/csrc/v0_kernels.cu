@@ -6,6 +6,8 @@
 //   uint64  t_total[np]
 //   int32   ep_step[np], ai_score[np], opp_score[np]
 //   uint8   owner[np], last_owner[np], flags[np]
+//   uint32  sched[64 + np / 32]   work queue of the time-sliced rollout (below): [0] next unit, [64 + w] chunks done by
+//                                 the envs of block-group w; zeroed by the launcher before every such launch
 // = 223 bytes per env.  Inside a kernel the 25 doubles of an environment sit in shared memory (one column
 // per lane, v0_step.cuh) and the scalars in registers; HBM is touched at the two ends of a launch only.
 #include <cuda_runtime.h>
@@ -18,12 +20,15 @@ namespace futbol {
 
 struct StateView {
     double *f; uint64_t *t_total; int32_t *ep_step, *ai_score, *opp_score; uint8_t *owner, *last_owner, *flags;
+    uint32_t *sched;
     size_t np;
 };
+constexpr int kSchedHead = 64;                                        // words before the per-group counters (256 B)
+__host__ __device__ inline size_t v0_sched_words(size_t np) { return kSchedHead + np / 32; }
 
 __host__ __device__ inline size_t v0_padded(int n) { return ((size_t)n + 255) & ~(size_t)255; }
 
-size_t v0_state_bytes(int n_envs) { return v0_padded(n_envs) * (25 * 8 + 8 + 3 * 4 + 3); }
+size_t v0_state_bytes(int n_envs) { return v0_padded(n_envs) * (25 * 8 + 8 + 3 * 4 + 3) + v0_sched_words(v0_padded(n_envs)) * 4; }
 
 __host__ __device__ inline StateView make_view(void *base, int n)
 {
@@ -37,7 +42,8 @@ __host__ __device__ inline StateView make_view(void *base, int n)
     v.opp_score = (int32_t *)p;   p += v.np * 4;
     v.owner = (uint8_t *)p;       p += v.np;
     v.last_owner = (uint8_t *)p;  p += v.np;
-    v.flags = (uint8_t *)p;
+    v.flags = (uint8_t *)p;       p += v.np;
+    v.sched = (uint32_t *)p;
     return v;
 }
 
@@ -47,14 +53,16 @@ __host__ __device__ inline StateView make_view(void *base, int n)
 constexpr int kEnvThreads = FUTBOL_ENV_THREADS;                   // threads per block of every env kernel
 constexpr int kEnvSmemBytes = (kEnvThreads / 32) * kWarpSmemBytes;   // dynamic shared memory per block
 
+// The loads go to L2 (ld.global.cg): in the time-sliced rollout another SM may have written this state a moment ago,
+// and L1 is not coherent.
 __device__ __forceinline__ void load_state(const StateView &v, int i, Lane L, V0Regs &s)
 {
     const double *f = v.f + i;
 #pragma unroll
-    for (int k = 0; k < 25; ++k) L.f(k * kLanes) = f[(size_t)k * v.np];
-    s.t_total = v.t_total[i];
-    s.ep_step = v.ep_step[i]; s.ai_score = v.ai_score[i]; s.opp_score = v.opp_score[i];
-    s.owner = v.owner[i]; s.last_owner = v.last_owner[i];
+    for (int k = 0; k < 25; ++k) L.f(k * kLanes) = __ldcg(f + (size_t)k * v.np);
+    s.t_total = __ldcg(v.t_total + i);
+    s.ep_step = __ldcg(v.ep_step + i); s.ai_score = __ldcg(v.ai_score + i); s.opp_score = __ldcg(v.opp_score + i);
+    s.owner = __ldcg(v.owner + i); s.last_owner = __ldcg(v.last_owner + i);
 }
 
 __device__ __forceinline__ void store_state(const StateView &v, int i, Lane L, const V0Regs &s, int flags)
@@ -77,8 +85,16 @@ __device__ __forceinline__ void warp_store_obs_f32(Lane L, const V0Regs &s, floa
 {
     __syncwarp();
     float *mine = stage + lane * kObsDim;
+    // one row (5 values) per trip: loads, conversions and stores of a row overlap, and the loop is a quarter of the
+    // unrolled code (instruction-cache footprint, r1_history.md r1i)
+#pragma unroll 1
+    for (int r = 0; r < 5; ++r) {
+        double d[5];
 #pragma unroll
-    for (int k = 0; k < 25; ++k) mine[k] = (float)L.f(k * kLanes);
+        for (int c = 0; c < 5; ++c) d[c] = L.f((5 * r + c) * kLanes);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) mine[5 * r + c] = (float)d[c];
+    }
 #pragma unroll
     for (int k = 0; k < 5; ++k) mine[25 + k] = (float)obs_owner_elem(s, k);
     __syncwarp();
@@ -167,12 +183,15 @@ __global__ void __launch_bounds__(kEnvThreads, FUTBOL_MIN_BLOCKS) v0_step_kernel
 
 // ---- fused K-step rollout ----------------------------------------------------------------------------
 
+// Steps [k0, k1) of the rollout for the 128 envs of block-group `group`: state HBM -> shared memory, the steps,
+// state back.  One call per block in the plain rollout; one call per work unit in the time-sliced one.
 template <bool RANDOM_OPP>
-__global__ void __launch_bounds__(kEnvThreads, FUTBOL_MIN_BLOCKS)
-v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ actions, const uint8_t *__restrict__ opp_actions,
-                  float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
+__device__ __forceinline__ void rollout_span(const V0Params &P, const StateView &v, int group, int k0, int k1,
+                                             const uint8_t *__restrict__ actions, const uint8_t *__restrict__ opp_actions,
+                                             float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done,
+                                             FutbolStats *stats)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = group * kEnvThreads + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warp_env0 = i - lane;
     if (warp_env0 >= P.n_envs) return;            // whole warp out of range
@@ -194,7 +213,7 @@ v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ ac
     int last_flags = 0;
 
 #pragma unroll 1
-    for (int k = 0; k < K; ++k) {
+    for (int k = k0; k < k1; ++k) {
         const size_t slot = (size_t)k * n + (size_t)i;
         int a;
         if (actions != nullptr) a = live ? (__ldg(actions + slot) & 15) : 0;
@@ -230,12 +249,58 @@ v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ ac
         }
         if (lane == 0) {
             atomicAdd(&stats->reward_sum, reward_sum);
-            atomicAdd((unsigned long long *)&stats->env_steps, (unsigned long long)rows_in_warp * (unsigned long long)K);
+            atomicAdd((unsigned long long *)&stats->env_steps, (unsigned long long)rows_in_warp * (unsigned long long)(k1 - k0));
             atomicAdd((unsigned long long *)&stats->episodes, (unsigned long long)episodes);
             atomicAdd((unsigned long long *)&stats->goals_ai, (unsigned long long)goals_ai);
             atomicAdd((unsigned long long *)&stats->goals_opp, (unsigned long long)goals_opp);
             atomicAdd((unsigned long long *)&stats->out_of_field, (unsigned long long)fixes);
         }
+    }
+}
+
+
+template <bool RANDOM_OPP>
+__global__ void __launch_bounds__(kEnvThreads, FUTBOL_MIN_BLOCKS)
+v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ actions, const uint8_t *__restrict__ opp_actions,
+                  float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
+{
+    rollout_span<RANDOM_OPP>(P, v, blockIdx.x, 0, K, actions, opp_actions, obs, reward, done, stats);
+}
+
+// Time-sliced rollout for batches of only a few waves of blocks (131,072 envs per GPU = 1024 blocks on 740 block slots:
+// the last 0.38 wave would run on a mostly idle GPU).  The K steps are cut into `chunks` slices of `chunk_steps`; a work
+// unit is (slice c, block-group g), numbered c * groups + g, and a grid that just fills the GPU takes units from a
+// counter.  Unit (c, g) needs (c - 1, g): that unit has a SMALLER number, so it was taken earlier by a block that is
+// running and never waits on a later unit -- no deadlock whatever the residency.  With groups >= grid it has normally
+// finished long ago; otherwise thread 0 polls the group's counter.  Hand-over of the state between blocks goes through
+// HBM/L2: writer __threadfence + barrier + counter store, reader counter load + __threadfence + barrier + ld.cg loads.
+template <bool RANDOM_OPP>
+__global__ void __launch_bounds__(kEnvThreads, FUTBOL_MIN_BLOCKS)
+v0_rollout_sliced_kernel(V0Params P, StateView v, int K, int chunk_steps, int chunks, int groups,
+                         const uint8_t *__restrict__ actions, const uint8_t *__restrict__ opp_actions,
+                         float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
+{
+    __shared__ uint32_t unit_s;
+    volatile uint32_t *progress = v.sched + kSchedHead;
+    const uint32_t units = (uint32_t)chunks * (uint32_t)groups;
+    for (;;) {
+        if (threadIdx.x == 0) unit_s = atomicAdd(v.sched, 1u);
+        __syncthreads();
+        const uint32_t u = unit_s;
+        if (u >= units) break;
+        const int c = (int)(u / (uint32_t)groups), g = (int)(u % (uint32_t)groups);
+        if (c > 0) {
+            if (threadIdx.x == 0) {
+                while (progress[g] < (uint32_t)c) __nanosleep(200);
+                __threadfence();
+            }
+        }
+        __syncthreads();                       // also keeps unit_s from being overwritten while others still read it
+        rollout_span<RANDOM_OPP>(P, v, g, c * chunk_steps, min(K, (c + 1) * chunk_steps), actions, opp_actions, obs, reward,
+                                 done, stats);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) progress[g] = (uint32_t)(c + 1);
     }
 }
 
@@ -296,14 +361,59 @@ cudaError_t v0_launch_step(const V0Params &P, void *state, const uint8_t *action
     return cudaGetLastError();
 }
 
+// resident blocks of the rollout kernels on the current device (SMs x blocks per SM), queried once per variant
+template <bool RANDOM_OPP>
+static int rollout_block_slots()
+{
+    static int slots = 0;
+    if (slots == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v0_rollout_sliced_kernel<RANDOM_OPP>, kEnvThreads, kEnvSmemBytes);
+        slots = sms * per_sm > 0 ? sms * per_sm : 1;
+    }
+    return slots;
+}
+
+template <bool RANDOM_OPP>
+static cudaError_t launch_rollout(const V0Params &P, const StateView &v, int K, const uint8_t *actions, const uint8_t *opp_actions,
+                                  float *obs, float *reward, uint8_t *done, FutbolStats *stats, int slices, cudaStream_t st)
+{
+    const int groups = blocks_for(P.n_envs, kEnvThreads);
+    const int slots = rollout_block_slots<RANDOM_OPP>();
+    // Plain launch when the batch is under one wave (nothing to balance) or many waves (the tail is a few percent).
+    // In between, slice the K steps so that the queue holds five to six waves of units: each unit pays one state round
+    // trip, and measured on a B200 (tools/time_rank_batch.py, K = 64) 4 slices are best for 131,072 envs (+18 % over
+    // the plain launch), 2 for 262,144 (+3 %); finer slicing loses more to the round trips than the shorter tail gains.
+    int chunks = 1;
+    if (slices > 0) chunks = slices < K ? slices : K;               // futbol_set_rollout_slices: tests, tuning
+    else if (groups > slots && groups < 6 * slots) {
+        chunks = (11 * slots + 2 * groups - 1) / (2 * groups);
+        if (chunks > K / 4) chunks = K / 4;
+    }
+    if (chunks < 1) chunks = 1;
+    if (chunks == 1) {
+        v0_rollout_kernel<RANDOM_OPP><<<groups, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+        return cudaGetLastError();
+    }
+    const int chunk_steps = (K + chunks - 1) / chunks;
+    chunks = (K + chunk_steps - 1) / chunk_steps;
+    cudaError_t e = cudaMemsetAsync(v.sched, 0, v0_sched_words(v.np) * 4, st);
+    if (e != cudaSuccess) return e;
+    const long long units = (long long)chunks * groups;
+    const int grid = (int)(units < slots ? units : slots);
+    v0_rollout_sliced_kernel<RANDOM_OPP><<<grid, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, chunk_steps, chunks, groups, actions,
+                                                                                 opp_actions, obs, reward, done, stats);
+    return cudaGetLastError();
+}
+
 cudaError_t v0_launch_rollout(const V0Params &P, void *state, int K, const uint8_t *actions, const uint8_t *opp_actions,
-                              float *obs, float *reward, uint8_t *done, FutbolStats *stats, cudaStream_t st)
+                              float *obs, float *reward, uint8_t *done, FutbolStats *stats, int slices, cudaStream_t st)
 {
     const StateView v = make_view(state, P.n_envs);
-    const int blocks = blocks_for(P.n_envs, kEnvThreads);
-    if (P.random_opp) v0_rollout_kernel<true><<<blocks, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
-    else v0_rollout_kernel<false><<<blocks, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
-    return cudaGetLastError();
+    return P.random_opp ? launch_rollout<true>(P, v, K, actions, opp_actions, obs, reward, done, stats, slices, st)
+                        : launch_rollout<false>(P, v, K, actions, opp_actions, obs, reward, done, stats, slices, st);
 }
 
 cudaError_t v0_launch_get_state(int n, const void *state, void *aos, cudaStream_t st)

@@ -12,7 +12,7 @@ cudaError_t v0_launch_reset(const V0Params &P, void *state, const uint8_t *mask,
 cudaError_t v0_launch_step(const V0Params &P, void *state, const uint8_t *actions, const uint8_t *opp_actions, void *obs,
                            void *reward, uint8_t *done, void *final_obs, int out_f64, cudaStream_t st);
 cudaError_t v0_launch_rollout(const V0Params &P, void *state, int K, const uint8_t *actions, const uint8_t *opp_actions,
-                              float *obs, float *reward, uint8_t *done, FutbolStats *stats, cudaStream_t st);
+                              float *obs, float *reward, uint8_t *done, FutbolStats *stats, int slices, cudaStream_t st);
 cudaError_t v0_launch_get_state(int n, const void *state, void *aos, cudaStream_t st);
 cudaError_t v0_launch_set_state(int n, void *state, const void *aos, cudaStream_t st);
 }  // namespace futbol

@@ -37,6 +37,7 @@ enum : int { kFlagGoal = 1, kFlagFix = 2, kFlagDone = 4 };
 constexpr double kFieldLen = 105.0, kFieldWid = 68.0;   // futbol_env.py:18-19
 constexpr double kGoalLower = 29.0, kGoalUpper = 39.0;  // :23-24
 constexpr double kStepSize = 0.1;                       // :45
+constexpr double kNaN = __builtin_nan("");
 
 // For s = fl(fl(dx*dx) + fl(dy*dy)) and d = sqrt_rn(s) (correctly rounded, hence monotone):
 //   d <= 1.0  <=>  s <= nextafter(1, +inf)
@@ -72,14 +73,12 @@ struct V0Params {
 // One block of kWarpSmemBytes per warp; element k of lane l of a section at section[k * kLanes + l].
 //   double  st[25][kLanes]   k = 5 * row + field, rows ai_1, ai_2, opp_1, opp_2, ball; fields x, y, tx, ty,
 //                            speed (= observation rows 0-4)
-//   then, overlapping in time:  uint32 draws[kDrawWords][kLanes] + double nb[2][kLanes] (during the step: the
-//                               Philox words and the ball's anticipated (x, y))
+//   then, overlapping in time:  uint32 draws[kDrawWords][kLanes]   (during the step: the Philox words)
 //                               float  stage[kLanes * 30]          (observation staging, after the step)
 constexpr int kStateWords = 25;
 constexpr int kObsDim = 30;
 constexpr int kWarpStateBytes = kStateWords * kLanes * 8;
-constexpr int kNbX = kStateWords + kDrawWords / 2, kNbY = kNbX + 1;       // element index (x kLanes) of the anticipated ball
-constexpr int kStepScratchBytes = kDrawWords * kLanes * 4 + 2 * kLanes * 8;
+constexpr int kStepScratchBytes = kDrawWords * kLanes * 4;
 constexpr int kWarpScratchBytes = (kLanes * kObsDim * 4 > kStepScratchBytes) ? kLanes * kObsDim * 4 : kStepScratchBytes;
 constexpr int kWarpSmemBytes = kWarpStateBytes + kWarpScratchBytes;
 constexpr int kX = 0, kY = kLanes, kTX = 2 * kLanes, kTY = 3 * kLanes, kSP = 4 * kLanes;   // field offsets in a row
@@ -118,7 +117,6 @@ struct V0Regs {
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 // c ? a : b that the optimiser cannot look through.  Used where a lane is handed a benign operand to keep
 // it on the fast path of the IEEE sqrt/div sequence: with a plain ternary the compiler rewrites
 // sqrt(c ? q : 1.0) into c ? sqrt(q) : 1.0 and the zero operand is back (seen in ncu as 1-6 lanes per warp
@@ -135,7 +133,6 @@ __device__ __forceinline__ double pick(bool c, double a, double b)
 inline double pick(bool c, double a, double b) { return c ? a : b; }
 #endif
 __device__ __forceinline__ double sqsum(double vx, double vy) { return dadd(dmul(vx, vx), dmul(vy, vy)); }
-__device__ __forceinline__ double hyp(double vx, double vy) { return __dsqrt_rn(sqsum(vx, vy)); }   // get_vec, :62-65
 
 // ---- specified elementary functions (domain: log on (0,1]; sin/cos on |x| <= 2*pi) --------------------
 __device__ __forceinline__ double fm_log(double x)
@@ -149,7 +146,7 @@ __device__ __forceinline__ double fm_log(double x)
     double m = __longlong_as_double((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
     if (m > 1.4142135623730951) { m = dmul(m, 0.5); k += 1; }
     const double f = dsub(m, 1.0);
-    const double s = ddiv(f, dadd(2.0, f));
+    const double s = fdiv(f, dadd(2.0, f));            // f is +0 or 2^-24 <= |f| <= 0.42, the divisor in [1.7, 2.42]
     const double z = dmul(s, s), w = dmul(z, z);
     const double t1 = dmul(w, dadd(Lg2, dmul(w, dadd(Lg4, dmul(w, Lg6)))));
     const double t2 = dmul(z, dadd(Lg1, dmul(w, dadd(Lg3, dmul(w, dadd(Lg5, dmul(w, Lg7)))))));
@@ -176,12 +173,11 @@ static __device__ __noinline__ void fm_sincos(double x, double &sn, double &cs)
     const double sr = dadd(r, dmul(v, dadd(S1, dmul(z, rs))));
     const double rc = dmul(z, dadd(C1, dmul(z, dadd(C2, dmul(z, dadd(C3, dmul(z, dadd(C4, dmul(z, dadd(C5, dmul(z, C6)))))))))));
     const double cr = dadd(dsub(1.0, dmul(0.5, z)), dmul(z, rc));
-    switch (n & 3) {
-    case 0: sn = sr; cs = cr; break;
-    case 1: sn = cr; cs = -sr; break;
-    case 2: sn = -sr; cs = -cr; break;
-    default: sn = -cr; cs = sr; break;
-    }
+    // quadrant n & 3:  0: (sr, cr)   1: (cr, -sr)   2: (-sr, -cr)   3: (-cr, sr)
+    const bool odd = (n & 1) != 0;
+    const double s0 = odd ? cr : sr, c0 = odd ? sr : cr;
+    sn = (n & 2) ? -s0 : s0;
+    cs = ((n + 1) & 2) ? -c0 : c0;
 }
 
 // kickoff formation, futbol_env.py:211-223 (also the goal re-kickoff :684-692).  Out of line: three call
@@ -317,7 +313,12 @@ __device__ __forceinline__ void resolve_shot(Lane L, const V0Regs &s, const V0Pa
     const double accuracy = dadd(10.0, dmul((double)near, 20.0));        // :364
     const int bo = kBallRow * kRowStride;
     const double vx = dsub(right ? 0.0 : kFieldLen, L.f(bo + kX)), vy = dsub((double)shot.target_y, L.f(bo + kY));   // :373-376
-    const double mag = hyp(vx, vy);
+    // The kicker holds the ball, so the ball is on the pitch and off the goal mouth it aims at: |v| > 0 (a ball at
+    // (0 | 105, 32..36) has scored, :581-582).  The guard-free sequences need just that; were it ever 0 the
+    // reference would divide 0 by 0, and so does this.
+    const double mag2 = sqsum(vx, vy);
+    const bool aimed = mag2 != 0.0;
+    const double mag = aimed ? fsqrt(pick(aimed, mag2, 1.0)) : 0.0;      // get_vec, :62-65
 
     const uint32_t pick_slot = __umulhi(L.draw(shot.pick_idx), 10u);     // randint(0, 9), :107
     const Philox4 nb = philox_step_block(P.key, env_id, kStreamDynamics, s.t_total, kNormalBlock0 + (pick_slot >> 1));
@@ -326,10 +327,13 @@ __device__ __forceinline__ void resolve_shot(Lane L, const V0Regs &s, const V0Pa
     const double u2 = (double)(w1 >> 8) * (1.0 / 16777216.0);
     double bm_sin, bm_cos;
     fm_sincos(dmul(6.283185307179586, u2), bm_sin, bm_cos);
-    const double z = dmul(__dsqrt_rn(dmul(-2.0, fm_log(u1))), bm_cos);
-    const double nd = dadd(0.0, dmul(accuracy, z));                      // np.random.normal(0, accuracy), :103
-    const double c = ddiv(dmul(vx, 1.0), mag), sn = ddiv(dmul(vy, 1.0), mag);  // :105-106
-    const double swing = dmul(ddiv(nd, 180.0), 3.141592653589793);       // :108
+    const double m2l = dmul(-2.0, fm_log(u1));                           // -0 for u1 == 1, else >= 1.19e-7
+    const double z = dmul(m2l == 0.0 ? m2l : fsqrt(pick(m2l != 0.0, m2l, 1.0)), bm_cos);
+    const double nd = dadd(0.0, dmul(accuracy, z));                      // np.random.normal(0, accuracy), :103; never -0
+    double c, sn;
+    fdiv2(dmul(vx, 1.0), dmul(vy, 1.0), pick(aimed, mag, 1.0), c, sn);   // :105-106 (numerators: never -0)
+    if (!aimed) c = sn = kNaN;
+    const double swing = dmul(fdiv(nd, 180.0), 3.141592653589793);       // :108 (|nd| is 0 or > 1e-16)
     double ss, sc;
     fm_sincos(swing, ss, sc);                                            // :109-110
     const double tc = dsub(dmul(c, sc), dmul(sn, ss));                   // :113
@@ -375,8 +379,9 @@ __device__ __forceinline__ void advance_xy(Lane L, int src, double &xo, double &
     yo = moving ? y1 : y;
 }
 
-// The kinematics phase, :661-663: all five rows in one straight-line block (independent rows: the scheduler is
-// free to overlap their sqrt / reciprocal chains).
+// The kinematics phase, :661-663: all five rows in one straight-line block (independent rows: the scheduler
+// overlaps their sqrt / reciprocal chains).  4.6 KB of code; a rolled loop over one out-of-line copy fits the
+// instruction cache better (hit rate 94.5 % -> 99.4 %) but is 3 % slower for the lost overlap (r1_history.md, r1i).
 __device__ __forceinline__ void advance_all(Lane L)
 {
     double nx[5], ny[5];
@@ -387,12 +392,12 @@ __device__ __forceinline__ void advance_all(Lane L)
 }
 
 // single row, out of line: the opponents' anticipation of the ball (:962-965)
-static __device__ __noinline__ void advance_row(Lane L, int src, int dx, int dy)
+struct XY { double x, y; };
+static __device__ __noinline__ XY advance_row(Lane L, int src)
 {
-    double xo, yo;
-    advance_xy(L, src, xo, yo);
-    L.f(dx) = xo;
-    L.f(dy) = yo;
+    XY o;
+    advance_xy(L, src, o.x, o.y);
+    return o;
 }
 
 __device__ __forceinline__ bool out_of_pitch(double x, double y)
@@ -444,8 +449,10 @@ __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params 
     } else {                                                             // _opp_team_set_vector_observation, :864-947
         has1 = s.owner == kOpp1; has2 = s.owner == kOpp2;                // :866-877 (latched before either acts)
         const bool team_has = has1 || has2;
-        const int a1 = easy_action(L, j, kOpp1, has1, team_has);         // :879
-        const int a2 = easy_action(L, j, kOpp2, has2, team_has);         // :880
+        int both = 0;                                                    // :879-880, one copy of the rule
+#pragma unroll 1
+        for (int o = 0; o < 2; ++o) both |= easy_action(L, j, kOpp1 + o, s.owner == kOpp1 + o, team_has) << (2 * o);
+        const int a1 = both & 3, a2 = both >> 2;
         run1 = a1 == kRun; run2 = a2 == kRun;
         opp_a1 = a1; opp_a2 = a2;                                        // overrides do not touch a1 / a2
         const double o1x = L.f(kOpp1 * kRowStride + kX), o1y = L.f(kOpp1 * kRowStride + kY);
@@ -473,8 +480,8 @@ __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params 
         player_turn(L, j, s, P, a, has_ball, action, set_target, t == 0 ? t1x : t2x, t == 0 ? t1y : t2y, shot);
         if (!RANDOM_OPP && t == 1) {
             // :962-982 anticipate the ball: whoever can reach its next position lands exactly on it
-            advance_row(L, bo, kNbX * kLanes, kNbY * kLanes);
-            const double nbx = L.f(kNbX * kLanes), nby = L.f(kNbY * kLanes);
+            const XY nb = advance_row(L, bo);
+            const double nbx = nb.x, nby = nb.y;
             const double v1x = dsub(nbx, L.f(kOpp1 * kRowStride + kX)), v1y = dsub(nby, L.f(kOpp1 * kRowStride + kY));
             const double v2x = dsub(nbx, L.f(kOpp2 * kRowStride + kX)), v2y = dsub(nby, L.f(kOpp2 * kRowStride + kY));
             const double q1 = sqsum(v1x, v1y), q2 = sqsum(v2x, v2y);

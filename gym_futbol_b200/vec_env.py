@@ -84,6 +84,10 @@ class FutbolVecEnv:
     def launch_count(self):
         return int(self.lib.futbol_launch_count(self._h))
 
+    def set_rollout_slices(self, slices):
+        """Time slicing of ``rollout`` (include/futbol_b200.h): 0 = automatic, 1 = off, n = n slices.  Results are identical."""
+        _lib.check(self.lib.futbol_set_rollout_slices(self._h, int(slices)))
+
     def _actions(self, actions, shape):
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions), device=self.device)

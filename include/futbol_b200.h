@@ -161,6 +161,14 @@ int futbol_selftest_arith(const double *a, const double *b, uint64_t *mismatch, 
 /* number of kernels this handle has launched (bench.py's gpu_launches) */
 uint64_t futbol_launch_count(const FutbolHandle *h);
 
+/* ---- launch tuning --------------------------------------------------------------------------
+ * futbol_rollout on a batch of only a few waves of thread blocks (e.g. 131,072 envs: one of eight ranks of the 2^20 job)
+ * cuts the K steps into time slices and lets a grid that just fills the GPU take (slice, env-block) units from a queue,
+ * so that no SM idles through a partial last wave.  Results do not depend on the slicing.  slices: 0 = chosen per
+ * launch from the batch size (default), 1 = never slice, n > 1 = n slices.  v0 only; ignored for v1.  No reference
+ * counterpart. */
+int futbol_set_rollout_slices(FutbolHandle *h, int slices);
+
 #ifdef __cplusplus
 }
 #endif

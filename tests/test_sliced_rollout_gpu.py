@@ -1,0 +1,68 @@
+"""Time-sliced rollout (futbol_set_rollout_slices, csrc/v0_kernels.cu): the work-queue launch must give the very
+bytes of the plain launch -- observations, rewards, dones, statistics and the final state -- whatever the number
+of slices, and agree with the oracle.  Small batches make every unit wait on its predecessor (fewer env-blocks than
+resident blocks), the 131,072-env case is the shape the slicing exists for (one of eight ranks of the 2^20 job)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(n, K, reps, slices, random_opp, seed=11, off=4242, acts=None, outputs=True):
+    import torch
+    from gym_futbol_b200 import FutbolVecEnv
+    env = FutbolVecEnv(n, seed=seed, env_id_offset=off, random_opp=random_opp, game_time=3.0)
+    env.set_rollout_slices(slices)
+    env.reset()
+    outs = []
+    for rep in range(reps):
+        a = None if acts is None else acts[rep]
+        if outputs:
+            o, r, d = env.rollout(K, actions=a)
+            outs.append((o.cpu().numpy().copy(), r.cpu().numpy().copy(), d.cpu().numpy().copy()))
+        else:
+            env.rollout(K, actions=a, obs=False, reward=False, done=False)
+    torch.cuda.synchronize()
+    return outs, env.get_state(), env.read_stats(), env.launch_count
+
+
+@pytest.mark.parametrize("random_opp", [False, True])
+@pytest.mark.parametrize("n,K,slices", [(4096 + 77, 64, 8), (4096 + 77, 64, 5), (513, 37, 37), (31, 20, 3)])
+def test_sliced_equals_plain(n, K, slices, random_opp):
+    plain = _run(n, K, 3, 1, random_opp)
+    sliced = _run(n, K, 3, slices, random_opp)
+    for (o0, r0, d0), (o1, r1, d1) in zip(plain[0], sliced[0]):
+        assert np.array_equal(o0.view(np.uint32), o1.view(np.uint32))
+        assert np.array_equal(r0.view(np.uint32), r1.view(np.uint32)) and np.array_equal(d0, d1)
+    assert plain[1].tobytes() == sliced[1].tobytes()
+    for key in ("env_steps", "episodes", "goals_ai", "goals_opp", "out_of_field"):
+        assert plain[2][key] == sliced[2][key]
+    assert abs(plain[2]["reward_sum"] - sliced[2]["reward_sum"]) <= 1e-9 * max(1.0, abs(plain[2]["reward_sum"]))
+    assert plain[3] == sliced[3]                                # one kernel per rollout either way
+
+
+def test_sliced_matches_oracle():
+    from oracle import philox
+    from oracle.v0 import OracleV0
+    n, K, reps, seed, off = 300, 48, 3, 5, 77
+    acts = [philox.actions_table(seed + 1, np.arange(off, off + n), rep * K, K) for rep in range(reps)]
+    outs, st, stats, _ = _run(n, K, reps, 6, False, seed=seed, off=off, acts=acts)
+    orc = OracleV0(n, seed=seed, env_id0=off, random_opp=False, game_time=3.0, arith=0)
+    for rep in range(reps):
+        want = orc.rollout(K, actions=acts[rep], autoreset=2, n_threads=4)
+        o, r, d = outs[rep]
+        assert np.array_equal(d, want["done"]) and np.array_equal(r, want["reward"].astype(np.float32))
+        assert np.array_equal(o, want["obs"].astype(np.float32))
+    assert np.array_equal(st["rows"].reshape(n, 25), orc.envs["obs"][:, :5].reshape(n, 25))
+    assert stats["env_steps"] == n * K * reps
+
+
+def test_rank_sized_batch_auto_slices():
+    """131,072 envs x K = 64 with the default setting (sliced on a B200: 1024 env-blocks on 740 slots) against the
+    plain launch: final states and statistics identical."""
+    n, K = 131072, 64
+    auto = _run(n, K, 2, 0, False, outputs=False)
+    plain = _run(n, K, 2, 1, False, outputs=False)
+    assert auto[1].tobytes() == plain[1].tobytes()
+    for key in ("env_steps", "episodes", "goals_ai", "goals_opp", "out_of_field"):
+        assert auto[2][key] == plain[2][key]
