@@ -212,12 +212,15 @@ __device__ __forceinline__ void rollout_span(const V0Params &P, const StateView 
     uint32_t episodes = 0, goals_ai = 0, goals_opp = 0, fixes = 0;
     int last_flags = 0;
 
+    int a_next = (actions != nullptr && live && k0 < k1) ? (int)__ldg(actions + (size_t)k0 * n + (size_t)i) : 0;
 #pragma unroll 1
     for (int k = k0; k < k1; ++k) {
         const size_t slot = (size_t)k * n + (size_t)i;
         int a;
-        if (actions != nullptr) a = live ? (__ldg(actions + slot) & 15) : 0;
-        else a = philox_action(P.key, env_id, s.t_total, 16);
+        if (actions != nullptr) {                 // this step's byte was requested one step ago: no wait on HBM here
+            a = a_next & 15;
+            if (live && k + 1 < k1) a_next = __ldg(actions + slot + n);
+        } else a = philox_action(P.key, env_id, s.t_total, 16);
         const int ai_before = s.ai_score;
         const int oa = (opp_actions != nullptr && live) ? (int)(__ldg(opp_actions + slot) & 15) : -1;
         const StepResult r = v0_step<RANDOM_OPP>(L, s, P, env_id, a, oa);
