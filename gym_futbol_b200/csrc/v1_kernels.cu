@@ -67,21 +67,41 @@ __device__ __forceinline__ void thread_store_obs(T *dst_row, Lane L, int N)
     for (int k = 0; k < D; ++k) dst_row[k] = (T)obs_elem(L, N, k);
 }
 
-// fp32 observations of a warp's 32 environments = one contiguous span of [n, D]: output element e belongs to
-// environment e / D of the warp, and every lane can read every lane's column (same warp, shared memory), so the
-// warp writes the span in order, 32 consecutive floats per instruction, without a staging copy.
+// fp32 observations of a warp's 32 environments = one contiguous span of [n, D].  Every lane can read every lane's
+// column (same warp, shared memory), so no staging copy is needed.  Lane l serves field l >> 3 (x, y, vx, vy) of
+// environment 8 g + (l & 7) in pass g: the field's average, range and the refined reciprocal of the range
+// (ieee_fast.cuh: same quotient as obs_elem's division) are then per-lane constants of the call, the body index is the
+// loop counter, and an instruction writes the four fields = 16 contiguous bytes of one body for eight environments
+// (the other bodies' stores complete the 32-byte sectors in L2).  The previous version wrote 32 consecutive floats
+// per instruction but spent 53 instructions per store on index arithmetic and a full division (r1_history.md, r1k).
 __device__ __forceinline__ void warp_store_obs_f32(Lane L, int N, float *gdst_warp_row0, int lane, int rows_in_warp)
 {
-    const int D = obs_dim(N);
+    const int D = obs_dim(N), B = 2 * N + 1;
     __syncwarp();                                     // every lane's step has finished writing its column
-    Lane other;
-    int env = lane / D, k = lane - env * D;
-    const int total = rows_in_warp * D;
-    for (int e = lane; e < total; e += 32) {
-        other.st = L.st - (uint32_t)lane + (uint32_t)env;
-        __stcs(gdst_warp_row0 + e, (float)obs_elem(other, N, k));
-        k += 32;
-        while (k >= D) { k -= D; env += 1; }
+    const int fld = lane >> 3, sub = lane & 7;
+    const double avg = fld == 0 ? 52.5 : (fld == 1 ? 34.0 : 0.0);
+    const double rng_ball = fld == 0 ? 52.5 : (fld == 1 ? 34.0 : 25.0), rng_player = fld == 0 ? 55.5 : (fld == 1 ? 34.0 : 10.0);
+    const double rcp_ball = frcp_refined(rng_ball), rcp_player = frcp_refined(rng_player);
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        const int env = 8 * g + sub;
+        if (env >= rows_in_warp) continue;
+        Lane src;                                     // field `fld` of body 0 of that environment's column
+        src.st = L.st - (uint32_t)lane + (uint32_t)(env + fld * kCol);
+        float *dst = gdst_warp_row0 + (size_t)env * D + fld;
+        {   // the ball leads the vector, :154-180
+            const double num = dsub(src.f(2 * N * kBodyStride), avg);
+            const bool z = num == 0.0;                               // 0 / range = that same zero (obs_elem)
+            const double q = fdiv_with(pick(z, 1.0, num), rng_ball, rcp_ball);
+            __stcs(dst, (float)(z ? num : q));
+        }
+#pragma unroll 1
+        for (int b = 0; b < B - 1; ++b) {
+            const double num = dsub(src.f(b * kBodyStride), avg);
+            const bool z = num == 0.0;
+            const double q = fdiv_with(pick(z, 1.0, num), rng_player, rcp_player);
+            __stcs(dst + 4 + 4 * b, (float)(z ? num : q));
+        }
     }
     __syncwarp();                                     // before the next step overwrites the columns
 }
