@@ -284,10 +284,24 @@ __device__ __forceinline__ void process_action(Lane L, V1Regs &s, const V1Params
             gx = L.f(tg * kBodyStride + kPX); gy = L.f(tg * kBodyStride + kPY); force = kBallForce - 20; div = 10.0;
         }
         const double vx = dsub(gx, L.f(bo + kPX)), vy = dsub(gy, L.f(bo + kPY));
-        const double kmag = dsqrt(dadd(dmul(vx, vx), dmul(vy, vy)));
-        const double bfx = ddiv(dmul(force, vx), kmag), bfy = ddiv(dmul(force, vy), kmag);
-        L.f(bo + kVX) = dadd(ddiv(L.f(bo + kVX), div), dmul(bfx, m_inv_b));
-        L.f(bo + kVY) = dadd(ddiv(L.f(bo + kVY), div), dmul(bfy, m_inv_b));
+        const double k2 = dadd(dmul(vx, vx), dmul(vy, vy));
+        if (k2 != 0.0) {
+            // guard-free sequences (ieee_fast.cuh): |v| is a pitch-scale distance; a zero numerator keeps its sign
+            // through the select; the ball's velocity is 0 or far above the sequences' lower bound
+            const double kmag = fsqrt(k2);
+            const double nx_ = dmul(force, vx), ny_ = dmul(force, vy), ovx = L.f(bo + kVX), ovy = L.f(bo + kVY);
+            const bool zx = nx_ == 0.0, zy = ny_ == 0.0, zvx = ovx == 0.0, zvy = ovy == 0.0;
+            double qx, qy, hx, hy;
+            fdiv2(pick(zx, 1.0, nx_), pick(zy, 1.0, ny_), kmag, qx, qy);
+            fdiv2(pick(zvx, 1.0, ovx), pick(zvy, 1.0, ovy), div, hx, hy);
+            L.f(bo + kVX) = dadd(zvx ? ovx : hx, dmul(zx ? nx_ : qx, m_inv_b));
+            L.f(bo + kVY) = dadd(zvy ? ovy : hy, dmul(zy ? ny_ : qy, m_inv_b));
+        } else {                                                         // kicked at a point exactly under the ball: 0 / 0 as in the reference
+            const double kmag = dsqrt(k2);
+            const double bfx = ddiv(dmul(force, vx), kmag), bfy = ddiv(dmul(force, vy), kmag);
+            L.f(bo + kVX) = dadd(ddiv(L.f(bo + kVX), div), dmul(bfx, m_inv_b));
+            L.f(bo + kVY) = dadd(ddiv(L.f(bo + kVY), div), dmul(bfy, m_inv_b));
+        }
     }
     if (touch) s.owner_side = side;                                      // :364, :414, :450-451
 }
@@ -408,8 +422,8 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
                 if (!(distsq < mind * mind)) continue;
                 if (nc == kMaxContacts) { overflow += 1; continue; }
                 Contact k;
-                const double dist = dsqrt(distsq);
-                if (dist != 0.0) { const double inv = ddiv(1.0, dist); k.nx = dmul(dx, inv); k.ny = dmul(dy, inv); }
+                const double dist = sqrt0(distsq);
+                if (dist != 0.0) { const double inv = fdiv(1.0, dist); k.nx = dmul(dx, inv); k.ny = dmul(dy, inv); }
                 else if (b >= 0) { k.nx = 1.0; k.ny = 0.0; }
                 else {   // segment normal: perp(normalize(b - a))
                     double sax, say, sbx, sby;
@@ -421,13 +435,15 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
                 const double p1x = dadd(pax, dmul(k.nx, ra)), p1y = dadd(pay, dmul(k.ny, ra));
                 const double p2x = dadd(tx, dmul(k.nx, -rb)), p2y = dadd(ty, dmul(k.ny, -rb));
                 const double pen = dadd(dmul(dsub(p2x, p1x), k.nx), dmul(dsub(p2y, p1y), k.ny));
-                const double ma = a == ball ? m_inv_b : m_inv_p, mb = b >= 0 ? (b == ball ? m_inv_b : m_inv_p) : 0.0;
-                k.n_mass = ddiv(1.0, dadd(ma, mb));
+                // 1 / (m_inv_a + m_inv_b): four possible pairs of masses, each quotient folded by the compiler (IEEE)
+                const double nm_pp = 1.0 / (m_inv_p + m_inv_p), nm_pb = 1.0 / (m_inv_p + m_inv_b), nm_ps = 1.0 / (m_inv_p + 0.0),
+                    nm_bs = 1.0 / (m_inv_b + 0.0);
+                k.n_mass = b >= 0 ? ((a == ball || b == ball) ? nm_pb : nm_pp) : (a == ball ? nm_bs : nm_ps);
                 double m = dadd(pen, kSlop);
                 m = m < 0.0 ? m : 0.0;                                   // cpfmin(0, dist + slop)
                 const double bnum = dmul(-P.bias_coef, m);               // -0.0 unless the pair overlaps by more than the slop
                 const bool bz = bnum == 0.0;
-                const double bq = ddiv(pick(bz, 1.0, bnum), kDt);
+                const double bq = fdiv(pick(bz, 1.0, bnum), kDt);
                 k.bias = bz ? bnum : bq;                                 // 0 / dt = that same zero, kept off the divider's slow path
                 k.jbias = 0.0;
                 const double vbx = b >= 0 ? L.f(b * kBodyStride + kVX) : 0.0, vby = b >= 0 ? L.f(b * kBodyStride + kVY) : 0.0;
