@@ -390,37 +390,66 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
     }
     // 2. narrow phase in pair-id order + 5. arbiter pre-step (uses the velocities before step 6)
     //    pass 0: circle/circle pairs (i < j), id j(j-1)/2 + i: outer loop over j, inner over i;
-    //    pass 1: circle/segment pairs, id CC + 12 * body + segment
+    //    pass 1: circle/segment pairs, id CC + 12 * body + segment.
+    //    Candidates, visited in ascending index (= ascending pair id).  Pass 0: every body i < jb.  Pass 1: only the
+    //    segments that can be reached at all -- r + r_segment <= 2.5, the left-hand segments {0, 1, 6, 7, 8} lie at
+    //    x <= 0, the right-hand ones {3, 4, 9, 10, 11} at x >= 105, segment 5 on y = 0 and segment 2 on y = 68 --
+    //    so a body strictly inside the pitch tests none and a body at a touchline tests one.
+    //    The scan only RECORDS the touching pairs (11 bits each, up to four pending in a register); their contacts are
+    //    built afterwards, all lanes together.  Built inside the scan, the 90-instruction block ran once for every
+    //    pair that touched in ANY of the warp's 32 environments (about six times a step for 2v2, twenty for 5v5) with
+    //    one or two lanes active; now it runs as many times as the busiest environment has contacts.
+    {
+        int pass = 0, jb = 1;
+        uint32_t cand = 1u;                                              // pass 0, jb = 1: body 0
+        double jx_ = L.f(kBodyStride + kPX), jy_ = L.f(kBodyStride + kPY);
+        bool scanning = true;
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
+        while (scanning) {
+            uint64_t hits = 0;
+            int nh = 0;
 #pragma unroll 1
-        for (int jb = pass == 0 ? 1 : 0; jb < B; ++jb) {
-            const int bo_j = jb * kBodyStride;
-            const double jx_ = L.f(bo_j + kPX), jy_ = L.f(bo_j + kPY);
-            // candidates, visited in ascending index (= ascending pair id).  Pass 0: every body i < jb.  Pass 1: only the
-            // segments that can be reached at all -- r + r_segment <= 2.5, the left-hand segments {0, 1, 6, 7, 8} lie at
-            // x <= 0, the right-hand ones {3, 4, 9, 10, 11} at x >= 105, segment 5 on y = 0 and segment 2 on y = 68 --
-            // so a body strictly inside the pitch tests none and a body at a touchline tests one.
-            uint32_t cand;
-            if (pass == 0) cand = (1u << jb) - 1u;
-            else cand = (jx_ < 2.5 ? 0x1C3u : 0u) | (jx_ > kWidth - 2.5 ? 0xE18u : 0u) | (jy_ < 2.5 ? 0x020u : 0u) | (jy_ > kHeight - 2.5 ? 0x004u : 0u);
-#pragma unroll 1
-            while (cand != 0u) {
+            while (nh < 4) {
+                if (cand == 0u) {                                        // next body, next pass
+                    jb += 1;
+                    if (jb >= B) { if (pass == 1) { scanning = false; break; } pass = 1; jb = 0; }
+                    jx_ = L.f(jb * kBodyStride + kPX); jy_ = L.f(jb * kBodyStride + kPY);
+                    if (pass == 0) cand = (1u << jb) - 1u;
+                    else cand = (jx_ < 2.5 ? 0x1C3u : 0u) | (jx_ > kWidth - 2.5 ? 0xE18u : 0u) | (jy_ < 2.5 ? 0x020u : 0u) | (jy_ > kHeight - 2.5 ? 0x004u : 0u);
+                    continue;
+                }
                 const int ii = __ffs((int)cand) - 1;
                 cand &= cand - 1u;
+                double tx, ty, pax, pay, mind;
+                if (pass == 0) {
+                    pax = L.f(ii * kBodyStride + kPX); pay = L.f(ii * kBodyStride + kPY); tx = jx_; ty = jy_;
+                    mind = kRPlayer + (jb == ball ? kRBall : kRPlayer);   // a = ii < jb: only b can be the ball
+                } else {
+                    pax = jx_; pay = jy_; seg_closest(ii, pax, pay, tx, ty);
+                    mind = (jb == ball ? kRBall : kRPlayer) + kRSeg;
+                }
+                const double dx = dsub(tx, pax), dy = dsub(ty, pay);
+                const double distsq = dadd(dmul(dx, dx), dmul(dy, dy));
+                if (!(distsq < mind * mind)) continue;
+                hits |= (uint64_t)((uint32_t)pass | ((uint32_t)jb << 1) | ((uint32_t)ii << 6)) << (16 * nh);
+                nh += 1;
+            }
+#pragma unroll 1
+            for (int h = 0; h < nh; ++h) {
+                const uint32_t code = (uint32_t)(hits >> (16 * h)) & 0xffffu;
+                const int hp = (int)(code & 1u), hj = (int)((code >> 1) & 31u), ii = (int)(code >> 6);
+                if (nc == kMaxContacts) { overflow += 1; continue; }
                 int a, b, q;                                             // b < 0: static segment -1 - b
-                if (pass == 0) { a = ii; b = jb; q = jb * (jb - 1) / 2 + ii; }
-                else { a = jb; b = -1 - ii; q = CC + jb * kNSeg + ii; }
+                if (hp == 0) { a = ii; b = hj; q = hj * (hj - 1) / 2 + ii; }
+                else { a = hj; b = -1 - ii; q = CC + hj * kNSeg + ii; }
                 const int ao = a * kBodyStride;
                 const double pax = L.f(ao + kPX), pay = L.f(ao + kPY);
                 const double ra = a == ball ? kRBall : kRPlayer;
                 double rb, tx, ty;                                       // (tx, ty): centre of b or closest point
-                if (b >= 0) { rb = b == ball ? kRBall : kRPlayer; tx = jx_; ty = jy_; }
+                if (b >= 0) { rb = b == ball ? kRBall : kRPlayer; tx = L.f(b * kBodyStride + kPX); ty = L.f(b * kBodyStride + kPY); }
                 else { rb = kRSeg; seg_closest(ii, pax, pay, tx, ty); }
                 const double dx = dsub(tx, pax), dy = dsub(ty, pay);
-                const double distsq = dadd(dmul(dx, dx), dmul(dy, dy)), mind = ra + rb;
-                if (!(distsq < mind * mind)) continue;
-                if (nc == kMaxContacts) { overflow += 1; continue; }
+                const double distsq = dadd(dmul(dx, dx), dmul(dy, dy));
                 Contact k;
                 const double dist = sqrt0(distsq);
                 if (dist != 0.0) { const double inv = fdiv(1.0, dist); k.nx = dmul(dx, inv); k.ny = dmul(dy, inv); }
