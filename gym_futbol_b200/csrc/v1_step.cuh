@@ -442,6 +442,10 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
                 int a, b, q;                                             // b < 0: static segment -1 - b
                 if (hp == 0) { a = ii; b = hj; q = hj * (hj - 1) / 2 + ii; }
                 else { a = hj; b = -1 - ii; q = CC + hj * kNSeg + ii; }
+                // cached arbiter of the pair, requested first: the ~90 instructions below run under the HBM latency
+                // (at the end of the block the two loads were 12 % of the 5v5 kernel's stall samples)
+                const uint32_t last = C.last[(size_t)q * C.stride];
+                const double cached = C.jn[(size_t)q * C.stride];
                 const int ao = a * kBodyStride;
                 const double pax = L.f(ao + kPX), pay = L.f(ao + kPY);
                 const double ra = a == ball ? kRBall : kRPlayer;
@@ -479,8 +483,6 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
                 const double el = b >= 0 ? kElasticity * kElasticity : kElasticity * 0.0;
                 k.bounce = dmul(dadd(dmul(dsub(vbx, L.f(ao + kVX)), k.nx), dmul(dsub(vby, L.f(ao + kVY)), k.ny)), el);
                 // cached arbiter (collision_persistence = 3): reuse the impulse of a pair that touched within 3 steps
-                const uint32_t last = C.last[(size_t)q * C.stride];   // both loads issued together: one HBM/L2 latency, not two
-                const double cached = C.jn[(size_t)q * C.stride];
                 k.jn = (s.stamp - last <= 3u) ? cached : 0.0;
                 C.last[(size_t)q * C.stride] = s.stamp;
                 if (REGC > 0 && nc == 0) c0 = k; else if (REGC > 1 && nc == 1) c1 = k; else con[nc - REGC] = k;

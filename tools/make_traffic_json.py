@@ -15,7 +15,9 @@ for arg in sys.argv[1:]:
     recs.append({"envs": int(envs), "K": int(K), "kernel": d[hdr.index("Kernel Name")],
                  "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
                  "dram_bytes": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
-                 "gpu_time_ms_under_ncu": float(d[hdr.index("gpu__time_duration.sum")]), "report": os.path.basename(rep)})
+                 "gpu_time_ms_under_ncu": float(d[hdr.index("gpu__time_duration.sum")]) *
+                 {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(units[hdr.index("gpu__time_duration.sum")].lower(), 1.0),
+                 "report": os.path.basename(rep)})
 json.dump({"launches": recs, "how": "ncu --set full --clock-control none, one launch each; dram__bytes_read.sum + dram__bytes_write.sum"},
           open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print(json.dumps(recs, indent=1))

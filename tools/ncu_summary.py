@@ -11,6 +11,8 @@ keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "sm__icc_request_hit_rate.pct", "sm__icc_requests.sum.pct_of_peak_sustained_elapsed",
+        "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed",
         "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum"]
 for r in rows[2:]:
     d = dict(zip(hdr, r))
