@@ -254,7 +254,11 @@ __global__ void v1_get_state_kernel(int n, int n_players, StateView v, FutbolV1E
 // ---- host launchers ------------------------------------------------------------------------------------
 static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 static inline int threads_for(int n_players) { return n_players <= 5 ? 64 : 32; }   // keeps a block under 48 KB of shared memory (10v10: 33 KB per warp)
-static inline int regc_for(int n_players) { return n_players >= 4 ? 2 : (n_players >= 2 ? 1 : 0); }   // contacts kept in registers by the solver (v1_step.cuh space_step)
+#ifdef FUTBOL_V1_REGC
+static inline int regc_for(int) { return FUTBOL_V1_REGC; }     // tuning builds (tools/build_variant.py)
+#else
+static inline int regc_for(int n_players) { return n_players >= 4 ? 2 : (n_players >= 2 ? 1 : 0); }
+#endif   // contacts kept in registers by the solver (v1_step.cuh space_step)
 static inline int smem_for(int n_players) { return block_smem_bytes(n_players, threads_for(n_players) / 32); }
 
 cudaError_t launch_reset(const V1Params &P, void *state, const uint8_t *mask, void *obs, int obs_f64, int init, cudaStream_t st)
