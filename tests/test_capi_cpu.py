@@ -45,6 +45,7 @@ def test_null_arguments_return_error_codes_without_a_gpu():
     assert L.futbol_reset(None, None, None, None, 0, None) == -1
     assert L.futbol_rollout(None, None, 4, None, None, None, None, None, None) == -1
     assert L.futbol_state_bytes(None) == 0
+    assert L.futbol_set_rollout_slices(None, 4) == -1
 
 
 def test_no_cpu_fallback():

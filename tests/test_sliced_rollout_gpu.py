@@ -66,3 +66,14 @@ def test_rank_sized_batch_auto_slices():
     assert auto[1].tobytes() == plain[1].tobytes()
     for key in ("env_steps", "episodes", "goals_ai", "goals_opp", "out_of_field"):
         assert auto[2][key] == plain[2][key]
+
+
+def test_slice_setting_is_validated():
+    from gym_futbol_b200 import FutbolError, FutbolVecEnv
+    env = FutbolVecEnv(64, seed=1)
+    with pytest.raises(FutbolError):
+        env.set_rollout_slices(-1)
+    env.set_rollout_slices(1000)                        # more slices than steps: clamped to one step per slice
+    env.reset()
+    o, r, d = env.rollout(8)
+    assert tuple(o.shape) == (8, 64, 30)
