@@ -8,6 +8,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+def _bits(a):
+    """The raw bytes of a float64 array: equal only if every value is the same BIT PATTERN (-0.0 != 0.0 here)."""
+    return np.ascontiguousarray(a, dtype=np.float64).tobytes()
+
+
 @pytest.mark.parametrize("random_opp", [False, True])
 def test_v0_soak_final_state_bit_exact(random_opp):
     import torch
@@ -23,7 +28,7 @@ def test_v0_soak_final_state_bit_exact(random_opp):
     torch.cuda.synchronize()
     st = env.get_state()
     e = orc.envs
-    assert np.array_equal(st["rows"].reshape(n, 25), e["obs"][:, :5].reshape(n, 25))
+    assert _bits(st["rows"].reshape(n, 25)) == _bits(e["obs"][:, :5].reshape(n, 25))           # the sign of zero included
     assert np.array_equal(st["owner"], e["owner"].astype(np.uint8)) and np.array_equal(st["last_owner"], e["last_owner"].astype(np.uint8))
     assert np.array_equal(st["ai_score"], e["ai_score"]) and np.array_equal(st["opp_score"], e["opp_score"])
     assert np.array_equal(st["t_total"], e["t_total"]) and (st["t_total"] == K * reps).all()
@@ -46,8 +51,8 @@ def test_v1_soak_final_state_bit_exact(N, n):
     torch.cuda.synchronize()
     st = env.get_state()
     B = 2 * N + 1
-    assert np.array_equal(st["body"][:, :B, 0:2], orc.envs["p"][:, :B]) and np.array_equal(st["body"][:, :B, 2:4], orc.envs["v"][:, :B])
-    assert np.array_equal(st["body"][:, :B, 4:6], orc.envs["vb"][:, :B])
+    assert _bits(st["body"][:, :B, 0:2]) == _bits(orc.envs["p"][:, :B]) and _bits(st["body"][:, :B, 2:4]) == _bits(orc.envs["v"][:, :B])
+    assert _bits(st["body"][:, :B, 4:6]) == _bits(orc.envs["vb"][:, :B])
     assert np.array_equal(st["owner_side"], orc.envs["owner_side"].astype(np.uint8)) and np.array_equal(st["ep_step"], orc.envs["ep_step"])
     stats = env.read_stats()
     assert stats["contacts_dropped"] == 0 and orc.envs["overflow"].sum() == 0 and stats["episodes"] == n * (K * reps // 300)
