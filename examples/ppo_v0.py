@@ -8,7 +8,7 @@ policy ([256, 256] shared, [128, 128] policy / value heads, colab_notebook.ipynb
     python examples/ppo_v0.py [--envs 65536] [--iters 3] [--steps 128]
 
 The policy needs obs_t to pick a_t, so the rollout uses the per-step API (one launch per step, state
-round-trips HBM); observations, rewards and dones never leave the device and the env's own output buffers
+round-trips HBM), replayed as one CUDA graph from the second iteration on; observations, rewards and dones never leave the device and the env's own output buffers
 are what the policy reads (asserted by data_ptr identity).  GAE runs on the device (futbol_gae).  Prints
 env-steps/s of the rollout alone and of rollout + update.  torch is the policy/optimiser library here; the
 simulator and the advantage kernel are this repository's CUDA.
@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--minibatches", type=int, default=4)
     ap.add_argument("--epochs", type=int, default=4)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--graph", type=int, default=1, help="replay the collection phase as one CUDA graph from the second iteration on")
     ap.add_argument("--bf16", type=int, default=1, help="run the torch policy under bf16 autocast (the simulator is fp64 either way)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -67,9 +68,9 @@ def main():
     val_buf = torch.empty((T + 1, n), device=dev)
     obs = env.reset()
     assert obs.data_ptr() == env.obs.data_ptr()            # the policy reads the simulator's buffer in place
-    for it in range(args.iters):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
+    def collect():
+        """T policy steps + T env steps + GAE, all enqueued on the current stream (no host synchronisation)."""
+        obs = env.obs
         with torch.no_grad():
             for t in range(T):
                 obs_buf[t].copy_(obs)
@@ -86,7 +87,26 @@ def main():
                 done_buf[t].copy_(done)
             with amp():
                 val_buf[T] = policy(obs)[1].float()
-            adv, ret = gae(rew_buf, done_buf, val_buf, 0.99, 0.95)
+            return gae(rew_buf, done_buf, val_buf, 0.99, 0.95)
+
+    graph = None
+    for it in range(args.iters):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if args.graph and it == 1:
+            # The whole collection phase (T x (policy forward, sampling, env step) + GAE: ~3000 launches) as ONE CUDA
+            # graph: the C ABI only enqueues on the caller's stream and every buffer is persistent, so it captures as is.
+            # Captured after one eager iteration (warm-up of cuBLAS / the allocator); the optimiser updates the weights
+            # in place, so replays see the current policy.  The capture itself is not timed.
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                adv, ret = collect()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        if graph is not None:
+            graph.replay()
+        else:
+            adv, ret = collect()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         flat = lambda x: x.reshape(T * n, *x.shape[2:])
