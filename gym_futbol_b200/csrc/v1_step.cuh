@@ -25,6 +25,10 @@ namespace futbol {
 namespace v1 {
 
 constexpr int kMaxN = 10, kMaxBodies = 2 * kMaxN + 1, kNSeg = 12, kMaxContacts = 32;
+#ifndef FUTBOL_V1_SOLVER_ITERS
+#define FUTBOL_V1_SOLVER_ITERS 10          // pymunk's Space.iterations default; other values only in timing builds (breaks parity)
+#endif
+constexpr int kSolverIterations = FUTBOL_V1_SOLVER_ITERS;
 constexpr double kWidth = 105.0, kHeight = 68.0, kGoalSize = 20.0, kDt = 0.1;      // futbol_env.py:19-26
 constexpr double kBallMaxV = 25.0, kPlayerMaxV = 10.0;                              // :31-32
 constexpr double kBallWeight = 10.0, kPlayerWeight = 20.0;                          // :34-35
@@ -508,7 +512,7 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
     // 8. ten iterations of cpArbiterApplyImpulse over the contacts in order
     if (nc > 0) {
 #pragma unroll 1
-        for (int it = 0; it < 10; ++it) {
+        for (int it = 0; it < kSolverIterations; ++it) {
             if (REGC > 0) solve_contact(L, c0, ball);
             if (REGC > 1 && nc > 1) solve_contact(L, c1, ball);
 #pragma unroll 1
