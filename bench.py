@@ -206,7 +206,26 @@ def run_reference_arm(args):
     base.update({"value": val, "ms_per_step": (dt / args.steps * 1e3) if dt else None,
                  "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                  "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(base), flush=True)
+    _emit(json.dumps(base))
+
+
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner from C when
+    NCCL_DEBUG is set on the box), so file descriptor 1 is pointed at stderr for the run and the result line goes to the
+    saved original."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (line + "\n").encode())
 
 
 # ----------------------------------------------------------------------------------- GPU arm
@@ -220,6 +239,7 @@ def main():
     ap.add_argument("--random-opp", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -399,7 +419,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_port_baseline()
-        print(json.dumps(out), flush=True)
+        _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
