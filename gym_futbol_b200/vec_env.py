@@ -38,6 +38,8 @@ class FutbolVecEnv:
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
             raise _lib.FutbolError("FutbolVecEnv needs a CUDA device; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_envs = int(num_envs)
         self.dtype = dtype
         self._dt = 1 if dtype == torch.float64 else 0
@@ -64,6 +66,13 @@ class FutbolVecEnv:
         self.stats = torch.zeros(_lib.STATS_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
         self._roll = {}
         self.episode_steps = self.lib.futbol_draw_limit_steps(h)
+        # step() is called once per environment step from Python: everything that does not change between calls is
+        # looked up once (the buffers above are persistent, so are their addresses)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._step_shape = (n,) + tuple(self.act_shape)
+        self._step_args = (self.state.data_ptr(), self.obs.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr(),
+                           self.final_obs.data_ptr())
+        self._step_info = {"terminal_observation": self.final_obs}
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -89,6 +98,9 @@ class FutbolVecEnv:
         _lib.check(self.lib.futbol_set_rollout_slices(self._h, int(slices)))
 
     def _actions(self, actions, shape):
+        if (type(actions) is torch.Tensor and actions.dtype == torch.uint8 and actions.device == self.device
+                and tuple(actions.shape) == shape and actions.is_contiguous()):
+            return actions                                # the usual case: already what the kernel reads
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions), device=self.device)
         if tuple(actions.shape) != shape:
@@ -110,12 +122,17 @@ class FutbolVecEnv:
     def step(self, actions, opp_actions=None):
         """actions: [n] ints in 0..15 (ai_1 = a // 4, ai_2 = a % 4).  opp_actions: None = the reference's own opponents;
         else the opponents' actions in the same format (self-play / learned opponents; v0 needs random_opp=True)."""
-        with torch.cuda.device(self.device):
-            a = self._actions(actions, (self.num_envs,) + self.act_shape)
-            o = None if opp_actions is None else self._actions(opp_actions, (self.num_envs,) + self.act_shape)
-            _lib.check(self.lib.futbol_step_vs(self._h, _ptr(self.state), _ptr(a), _ptr(o), _ptr(self.obs), _ptr(self.rewards),
-                                               _ptr(self.dones), _ptr(self.final_obs), self._dt, self._stream()))
-        return self.obs, self.rewards, self.dones, {"terminal_observation": self.final_obs}
+        if torch.cuda.current_device() != self._dev_index:
+            with torch.cuda.device(self.device):
+                return self.step(actions, opp_actions)
+        a = self._actions(actions, self._step_shape)
+        o = None if opp_actions is None else self._actions(opp_actions, self._step_shape).data_ptr()
+        st, ob, rw, dn, fo = self._step_args
+        rc = self.lib.futbol_step_vs(self._h, st, a.data_ptr(), o, ob, rw, dn, fo, self._dt,
+                                     torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            _lib.check(rc)
+        return self.obs, self.rewards, self.dones, self._step_info
 
     def rollout(self, K, actions=None, obs=True, reward=True, done=True, out=None, opp_actions=None):
         """K fused steps.  actions: uint8 [K, n] or None (uniform random actions drawn in-kernel).
@@ -210,6 +227,8 @@ class FutbolV1VecEnv(FutbolVecEnv):
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
             raise _lib.FutbolError("FutbolV1VecEnv needs a CUDA device; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_envs, self.number_of_player = int(num_envs), int(number_of_player)
         self.dtype = dtype
         self._dt = 1 if dtype == torch.float64 else 0
