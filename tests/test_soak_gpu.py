@@ -56,3 +56,34 @@ def test_v1_soak_final_state_bit_exact(N, n):
     assert np.array_equal(st["owner_side"], orc.envs["owner_side"].astype(np.uint8)) and np.array_equal(st["ep_step"], orc.envs["ep_step"])
     stats = env.read_stats()
     assert stats["contacts_dropped"] == 0 and orc.envs["overflow"].sum() == 0 and stats["episodes"] == n * (K * reps // 300)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(seed=1, random_opp=False, one_goal_end=True, game_time=25.0),
+    dict(seed=2, random_opp=True, only_reward_goal=True, game_time=12.5),
+    dict(seed=3, random_opp=False, player_speed=9.0, shoot_speed=24, game_time=40.0),
+    dict(seed=4, random_opp=True, player_speed=15.5, shoot_speed=17, one_goal_end=True, game_time=7.3),
+    dict(seed=2 ** 40 + 5, random_opp=False, player_speed=12.0, shoot_speed=20, game_time=0.0),
+    dict(seed=6, random_opp=False, only_reward_goal=True, one_goal_end=True, game_time=60.0),
+])
+def test_v0_constructor_options_at_scale(cfg):
+    """Every constructor option of FutbolEnv (futbol_env.py:134-138) away from its default, 4096 envs x 600 fused steps
+    with recorded rewards and dones, and a 64-bit seed: rewards and dones every step, final state bit pattern."""
+    import torch
+    from gym_futbol_b200 import FutbolVecEnv
+    from oracle.v0 import OracleV0
+    n, K, reps, off = 4096, 150, 4, 31337
+    env = FutbolVecEnv(n, env_id_offset=off, **cfg)
+    env.reset()
+    orc = OracleV0(n, env_id0=off, arith=0, **{k: (float(v) if k in ("player_speed", "shoot_speed") else v) for k, v in cfg.items()})
+    for _ in range(reps):
+        _, rew, done = env.rollout(K, obs=False)
+        want = orc.rollout(K, actions=None, autoreset=2, n_threads=16)
+        assert np.array_equal(done.cpu().numpy(), want["done"])
+        assert np.array_equal(rew.cpu().numpy(), want["reward"].astype(np.float32))
+    torch.cuda.synchronize()
+    st = env.get_state()
+    e = orc.envs
+    assert _bits(st["rows"].reshape(n, 25)) == _bits(e["obs"][:, :5].reshape(n, 25))
+    assert np.array_equal(st["ai_score"], e["ai_score"]) and np.array_equal(st["opp_score"], e["opp_score"])
+    assert np.array_equal(st["owner"], e["owner"].astype(np.uint8)) and np.array_equal(st["last_owner"], e["last_owner"].astype(np.uint8))
