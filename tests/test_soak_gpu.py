@@ -87,3 +87,27 @@ def test_v0_constructor_options_at_scale(cfg):
     assert _bits(st["rows"].reshape(n, 25)) == _bits(e["obs"][:, :5].reshape(n, 25))
     assert np.array_equal(st["ai_score"], e["ai_score"]) and np.array_equal(st["opp_score"], e["opp_score"])
     assert np.array_equal(st["owner"], e["owner"].astype(np.uint8)) and np.array_equal(st["last_owner"], e["last_owner"].astype(np.uint8))
+
+
+@pytest.mark.parametrize("N,n,total_time", [(3, 2048, 30.0), (4, 1024, 12.5), (6, 1024, 30.0), (7, 512, 5.0), (8, 512, 30.0), (9, 256, 30.0),
+                                            (10, 512, 30.0), (1, 4096, 3.1)])
+def test_v1_every_team_size_and_time_limit(N, n, total_time):
+    """Team sizes the other GPU tests skip (3, 4, 6-9: the three formation families of team.py:52-112) and time limits away
+    from the default: observations, rewards and dones of a fused rollout against the oracle, final bodies bit pattern."""
+    import torch
+    from gym_futbol_b200 import FutbolV1VecEnv
+    from oracle.v1 import OracleV1
+    K, seed, off = 340, 21, 808
+    env = FutbolV1VecEnv(n, number_of_player=N, seed=seed, env_id_offset=off, total_time=total_time)
+    orc = OracleV1(n, seed=seed, env_id0=off, number_of_player=N, total_time=total_time)
+    env.reset()
+    obs, rew, done = env.rollout(K)
+    want = orc.rollout(K, actions=None, autoreset=2, n_threads=16)
+    assert np.array_equal(done.cpu().numpy(), want["done"]) and int(want["done"].sum()) > 0
+    assert np.array_equal(rew.cpu().numpy(), want["reward"].astype(np.float32))
+    assert np.array_equal(obs.cpu().numpy(), want["obs"].astype(np.float32))
+    torch.cuda.synchronize()
+    st = env.get_state()
+    B = 2 * N + 1
+    assert _bits(st["body"][:, :B, 0:2]) == _bits(orc.envs["p"][:, :B]) and _bits(st["body"][:, :B, 2:4]) == _bits(orc.envs["v"][:, :B])
+    assert env.read_stats()["contacts_dropped"] == 0
