@@ -9,8 +9,9 @@ from gym_futbol_b200 import FutbolVecEnv
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-for n in (131072, 262144, 524288):
-    for slices in (1, 0, 2, 3, 4, 6, 8):
+sizes = [int(x) for x in os.environ.get("SIZES", "131072,262144,524288").split(",")]
+for n in sizes:
+    for slices in [int(x) for x in os.environ.get("SLICES", "1,0,2,3,4,6,8").split(",")]:
         env = FutbolVecEnv(n, seed=0, random_opp=False)
         env.set_rollout_slices(slices)
         env.reset()
