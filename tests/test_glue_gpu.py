@@ -75,3 +75,18 @@ def test_step_outputs_are_the_env_buffers(torch_cuda):
         obs, rew, done, info = env.step(torch.zeros(256, dtype=torch.uint8, device="cuda"))
         assert obs.data_ptr() == p0 == env.obs.data_ptr() and rew.data_ptr() == env.rewards.data_ptr()
         assert obs.is_cuda and rew.is_cuda and done.is_cuda and info["terminal_observation"].is_cuda
+
+
+def test_replay_of_a_rollout_buffer(torch_cuda, tmp_path):
+    """An env's trajectory cut out of the CUDA rollout buffer equals the per-step states of that env."""
+    from gym_futbol_b200 import FutbolVecEnv
+    from gym_futbol_b200.replay import save_gif, trajectory
+    n, K, i = 64, 40, 17
+    env = FutbolVecEnv(n, seed=3, random_opp=False, dtype=torch_cuda.float64)
+    env.reset()
+    obs, _, _ = env.rollout(K)
+    t = trajectory(obs, env=i, variant="v0")
+    o = obs[:, i].cpu().numpy().astype(np.float64)
+    assert np.array_equal(t["ball"], o[:, 20:22]) and np.array_equal(t["team_b"][:, 1], o[:, 15:17])
+    assert ((t["owner"] >= 0) & (t["owner"] <= 4)).all()
+    assert save_gif(str(tmp_path / "r.gif"), t, scale=3) == K
