@@ -257,7 +257,7 @@ static inline int threads_for(int n_players) { return n_players <= 5 ? 64 : 32; 
 #ifdef FUTBOL_V1_REGC
 static inline int regc_for(int) { return FUTBOL_V1_REGC; }     // tuning builds (tools/build_variant.py)
 #else
-static inline int regc_for(int n_players) { return n_players >= 4 ? 2 : (n_players >= 2 ? 1 : 0); }
+static inline int regc_for(int n_players) { return n_players >= 7 ? 3 : (n_players >= 4 ? 2 : (n_players >= 2 ? 1 : 0)); }
 #endif   // contacts kept in registers by the solver (v1_step.cuh space_step)
 static inline int smem_for(int n_players) { return block_smem_bytes(n_players, threads_for(n_players) / 32); }
 
@@ -284,8 +284,8 @@ cudaError_t launch_step(const V1Params &P, void *state, const uint8_t *actions, 
     const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
     const int g = blocks_for(P.n_envs, t), rc = regc_for(P.n_players);
 #define FUTBOL_V1_STEP(T, RC) v1_step_kernel<T, RC><<<g, t, sm, st>>>(P, v, actions, opp_actions, (T *)obs, (T *)reward, done, (T *)final_obs)
-    if (out_f64) { if (rc == 2) FUTBOL_V1_STEP(double, 2); else if (rc == 1) FUTBOL_V1_STEP(double, 1); else FUTBOL_V1_STEP(double, 0); }
-    else { if (rc == 2) FUTBOL_V1_STEP(float, 2); else if (rc == 1) FUTBOL_V1_STEP(float, 1); else FUTBOL_V1_STEP(float, 0); }
+    if (out_f64) { if (rc == 3) FUTBOL_V1_STEP(double, 3); else if (rc == 2) FUTBOL_V1_STEP(double, 2); else if (rc == 1) FUTBOL_V1_STEP(double, 1); else FUTBOL_V1_STEP(double, 0); }
+    else { if (rc == 3) FUTBOL_V1_STEP(float, 3); else if (rc == 2) FUTBOL_V1_STEP(float, 2); else if (rc == 1) FUTBOL_V1_STEP(float, 1); else FUTBOL_V1_STEP(float, 0); }
 #undef FUTBOL_V1_STEP
     return cudaGetLastError();
 }
@@ -296,7 +296,8 @@ cudaError_t launch_rollout(const V1Params &P, void *state, int K, const uint8_t 
     const StateView v = make_view(state, P.n_envs, P.n_players);
     const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
     const int g = blocks_for(P.n_envs, t), rc = regc_for(P.n_players);
-    if (rc == 2) v1_rollout_kernel<2><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+    if (rc == 3) v1_rollout_kernel<3><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+    else if (rc == 2) v1_rollout_kernel<2><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
     else if (rc == 1) v1_rollout_kernel<1><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
     else v1_rollout_kernel<0><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
     return cudaGetLastError();

@@ -373,17 +373,18 @@ __device__ __forceinline__ void warm_start_contact(Lane L, const Contact &k, int
 // The first two contacts of a step live in registers (c0, c1), the rest in the local-memory list `con` (index
 // i - 2): a step rarely has more than two, and the ten solver iterations would otherwise wait on local-memory
 // loads (L1 is small next to 200 KB of shared memory: ncu showed 53 % of the long-scoreboard stalls there).
-// REGC = how many contacts are register-resident, chosen by measurement: 2 for N >= 4, 1 for N = 2, 3 (a second
-// one costs more occupancy than its loads cost time: 2v2 -20 %), 0 for 1v1 (-14 % with one).
+// REGC = how many contacts are register-resident, chosen by measurement (end of round 1, env-steps/s): 0 for 1v1 (one
+// costs 2 %), 1 for N = 2, 3 (a second one costs occupancy: 2v2 -20 %), 2 for N = 4 ... 6, 3 for N >= 7 (+3 % at 7v7 and
+// 10v10, -1 % at 5v5).
 template <int REGC>
 __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, const PairCache &C, Contact *con, int &overflow)
 {
     const int N = P.n_players, B = 2 * N + 1, ball = 2 * N, CC = B * (B - 1) / 2;
     const double m_inv_p = 1.0 / kPlayerWeight, m_inv_b = 1.0 / kBallWeight;
     int nc = 0;
-    Contact c0, c1;
+    Contact c0, c1, c2;
     c0.a = c0.b = c0.q = 0; c1.a = c1.b = c1.q = 0;
-    c0.nx = c0.ny = c0.n_mass = c0.bias = c0.bounce = c0.jn = c0.jbias = 0.0; c1 = c0;
+    c0.nx = c0.ny = c0.n_mass = c0.bias = c0.bounce = c0.jn = c0.jbias = 0.0; c1 = c0; c2 = c0;
     // 1. integrate positions (cpBodyUpdatePosition): p += (v + v_bias) dt; v_bias = 0
 #pragma unroll 1
     for (int i = 0; i < B; ++i) {
@@ -489,7 +490,8 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
                 // cached arbiter (collision_persistence = 3): reuse the impulse of a pair that touched within 3 steps
                 k.jn = (s.stamp - last <= 3u) ? cached : 0.0;
                 C.last[(size_t)q * C.stride] = s.stamp;
-                if (REGC > 0 && nc == 0) c0 = k; else if (REGC > 1 && nc == 1) c1 = k; else con[nc - REGC] = k;
+                if (REGC > 0 && nc == 0) c0 = k; else if (REGC > 1 && nc == 1) c1 = k; else if (REGC > 2 && nc == 2) c2 = k;
+                else con[nc - REGC] = k;
                 nc += 1;
             }
         }
@@ -507,6 +509,7 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
     // 7. warm start (cpArbiterApplyCachedImpulse, dt_coef = 1)
     if (REGC > 0 && nc > 0) warm_start_contact(L, c0, ball);
     if (REGC > 1 && nc > 1) warm_start_contact(L, c1, ball);
+    if (REGC > 2 && nc > 2) warm_start_contact(L, c2, ball);
 #pragma unroll 1
     for (int i = REGC; i < nc; ++i) warm_start_contact(L, con[i - REGC], ball);
     // 8. ten iterations of cpArbiterApplyImpulse over the contacts in order
@@ -515,11 +518,13 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
         for (int it = 0; it < kSolverIterations; ++it) {
             if (REGC > 0) solve_contact(L, c0, ball);
             if (REGC > 1 && nc > 1) solve_contact(L, c1, ball);
+            if (REGC > 2 && nc > 2) solve_contact(L, c2, ball);
 #pragma unroll 1
             for (int i = REGC; i < nc; ++i) solve_contact(L, con[i - REGC], ball);
         }
         if (REGC > 0) C.jn[(size_t)c0.q * C.stride] = c0.jn;
         if (REGC > 1 && nc > 1) C.jn[(size_t)c1.q * C.stride] = c1.jn;
+        if (REGC > 2 && nc > 2) C.jn[(size_t)c2.q * C.stride] = c2.jn;
 #pragma unroll 1
         for (int i = REGC; i < nc; ++i) C.jn[(size_t)con[i - REGC].q * C.stride] = con[i - REGC].jn;
     }
