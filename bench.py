@@ -408,7 +408,8 @@ def main():
             "gpu_launches": int(launches), "gpu_launches_e2e": int(e2e_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(n_local, K), "peak_source": peak_src, "kernel": "v0_rollout_kernel",
+                         "traffic": measured_traffic(n_local, K), "peak_source": peak_src, "kernel": ("v0_rollout_sliced_kernel (the same step code; (time slice, env block) units from a work queue)"
+                                    if 740 < (n_local + 127) // 128 < 6 * 740 else "v0_rollout_kernel"),
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": n_local * K * BYTES_PER_ENV_STEP,
                          "note": "the kernel is instruction-issue bound (fp64 IEEE sqrt/div sequences, selects, Philox), "
