@@ -129,8 +129,11 @@ int futbol_create(const FutbolConfig *cfg, FutbolHandle **out)
         Q.n_players = cfg->n_players;
         Q.ep_limit = episode_limit_v1(cfg->game_time);
         Q.auto_reset = cfg->auto_reset != 0;
-        Q.damping_dt = pow(0.95, 0.1);                               // space.damping ** TIME_STEP
-        Q.bias_coef = 1.0 - pow(pow(1.0 - 0.1, 60.0), 0.1);          // Chipmunk's default collision_bias
+        // Literals, not pow() calls: the compiler may fold pow() of constants with correct rounding while Chipmunk
+        // and CPython call the C library at run time (glibc pow is not correctly rounded).  These are the run-time
+        // values (tests/test_oracle_v1_golden.py checks them against math.pow and the oracle's configuration).
+        Q.damping_dt = 0x1.fd6168eb56e59p-1;     // pow(0.95, 0.1): space.damping ** TIME_STEP (:99)
+        Q.bias_coef = 0x1.dfcdf3e02c8a4p-2;      // 1 - pow(pow(1.0f - 0.1f, 60.0f), 0.1): cpSpace.c's default collision_bias
         formation_v1(cfg->n_players, false, Q.form_x, Q.form_y);
         formation_v1(cfg->n_players, true, Q.form_x + cfg->n_players, Q.form_y + cfg->n_players);
     }

@@ -34,7 +34,7 @@ constexpr double kBallMaxV = 25.0, kPlayerMaxV = 10.0;                          
 constexpr double kBallWeight = 10.0, kPlayerWeight = 20.0;                          // :34-35
 constexpr double kPlayerForce = 40.0, kBallForce = 120.0;                           // :37-38
 constexpr double kRPlayer = 1.5, kRBall = 1.0, kRSeg = 1.0, kElasticity = 0.2;      // player.py:7, ball.py:7, :187
-constexpr double kSlop = 0.1;                                                       // Chipmunk collision_slop
+constexpr double kSlop = (double)0.1f;                                              // Chipmunk collision_slop: cpSpace.c writes the float literal 0.1f
 enum : int { kFlagGoal = 1, kFlagOut = 2, kFlagDone = 4, kFlagGoalLeft = 8 };
 constexpr uint32_t kResetBlock = 0x4000u;   // Philox block of the side drawn by reset()
 constexpr uint32_t kStamp0 = 8;             // first space-step stamp (cache entries start at 0 = "never touched")
@@ -71,7 +71,7 @@ struct V1Params {
     int ep_limit;         // first k with k additions of 0.1 > total_time (300 for 30), :478-481
     int auto_reset;
     double damping_dt;    // pow(0.95, 0.1): space.damping ** dt, :99
-    double bias_coef;     // 1 - pow(pow(0.9, 60), 0.1): Chipmunk collision_bias default
+    double bias_coef;     // 1 - pow(pow(1.0f - 0.1f, 60), 0.1): Chipmunk collision_bias default (float literals, cpSpace.c)
     double form_x[2 * kMaxN], form_y[2 * kMaxN];   // kick-off formation, team.py:52-112
 };
 
@@ -118,7 +118,10 @@ struct V1Regs {
     int ep_step, owner_side;
 };
 
+// q: pair id, plus kWarmBit when the pair also touched in the previous space step (arbiter state NORMAL: only those are
+// warm-started, cpArbiterApplyCachedImpulse returns early for FIRST_COLLISION)
 struct Contact { double nx, ny, n_mass, bias, bounce, jn, jbias; int a, b, q; };
+constexpr int kWarmBit = 0x8000, kPairMask = 0x7fff;
 
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
@@ -358,6 +361,7 @@ __device__ __forceinline__ void solve_contact(Lane L, Contact &k, int ball)
 // warm start of one contact (cpArbiterApplyCachedImpulse, dt_coef = 1)
 __device__ __forceinline__ void warm_start_contact(Lane L, const Contact &k, int ball)
 {
+    if (!(k.q & kWarmBit)) return;
     const double m_inv_p = 1.0 / kPlayerWeight, m_inv_b = 1.0 / kBallWeight;
     const double jx = dmul(k.nx, k.jn), jy = dmul(k.ny, k.jn), ma = k.a == ball ? m_inv_b : m_inv_p;
     const int ao = k.a * kBodyStride;
@@ -469,7 +473,7 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
                     const double sx = dsub(sbx, sax), sy = dsub(sby, say), sl = dsqrt(dadd(dmul(sx, sx), dmul(sy, sy)));
                     k.nx = -ddiv(sy, sl); k.ny = ddiv(sx, sl);
                 }
-                k.a = a; k.b = b; k.q = q;
+                k.a = a; k.b = b;
                 const double p1x = dadd(pax, dmul(k.nx, ra)), p1y = dadd(pay, dmul(k.ny, ra));
                 const double p2x = dadd(tx, dmul(k.nx, -rb)), p2y = dadd(ty, dmul(k.ny, -rb));
                 const double pen = dadd(dmul(dsub(p2x, p1x), k.nx), dmul(dsub(p2y, p1y), k.ny));
@@ -487,8 +491,10 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
                 const double vbx = b >= 0 ? L.f(b * kBodyStride + kVX) : 0.0, vby = b >= 0 ? L.f(b * kBodyStride + kVY) : 0.0;
                 const double el = b >= 0 ? kElasticity * kElasticity : kElasticity * 0.0;
                 k.bounce = dmul(dadd(dmul(dsub(vbx, L.f(ao + kVX)), k.nx), dmul(dsub(vby, L.f(ao + kVY)), k.ny)), el);
-                // cached arbiter (collision_persistence = 3): reuse the impulse of a pair that touched within 3 steps
+                // cached arbiter (collision_persistence = 3): a pair that touched within 3 steps inherits its impulse;
+                // it is warm-started with it only if it touched in the previous step too
                 k.jn = (s.stamp - last <= 3u) ? cached : 0.0;
+                k.q = q | (s.stamp - last == 1u ? kWarmBit : 0);
                 C.last[(size_t)q * C.stride] = s.stamp;
                 if (REGC > 0 && nc == 0) c0 = k; else if (REGC > 1 && nc == 1) c1 = k; else if (REGC > 2 && nc == 2) c2 = k;
                 else con[nc - REGC] = k;
@@ -522,11 +528,11 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
 #pragma unroll 1
             for (int i = REGC; i < nc; ++i) solve_contact(L, con[i - REGC], ball);
         }
-        if (REGC > 0) C.jn[(size_t)c0.q * C.stride] = c0.jn;
-        if (REGC > 1 && nc > 1) C.jn[(size_t)c1.q * C.stride] = c1.jn;
-        if (REGC > 2 && nc > 2) C.jn[(size_t)c2.q * C.stride] = c2.jn;
+        if (REGC > 0) C.jn[(size_t)(c0.q & kPairMask) * C.stride] = c0.jn;
+        if (REGC > 1 && nc > 1) C.jn[(size_t)(c1.q & kPairMask) * C.stride] = c1.jn;
+        if (REGC > 2 && nc > 2) C.jn[(size_t)(c2.q & kPairMask) * C.stride] = c2.jn;
 #pragma unroll 1
-        for (int i = REGC; i < nc; ++i) C.jn[(size_t)con[i - REGC].q * C.stride] = con[i - REGC].jn;
+        for (int i = REGC; i < nc; ++i) C.jn[(size_t)(con[i - REGC].q & kPairMask) * C.stride] = con[i - REGC].jn;
     }
     s.stamp += 1;
     return nc;

@@ -3,15 +3,19 @@
  * team.py, player.py, ball.py, plus the subset of Chipmunk2D 7.0.x (pymunk 5.6.0, the version the
  * reference's authors ran: colab_notebook.ipynb:118,130) that those files drive.
  *
- * TEST INFRASTRUCTURE (see oracle/README.md).  PARITY UNPINNED: pymunk/Chipmunk is a third-party
- * dependency that is neither vendored in /root/reference nor installable here, and the reference has no
- * test or golden vector at this boundary.  The physics below restates Chipmunk's published algorithm
- * (cpSpaceStep: position integration, circle/circle and circle/segment narrow phase, arbiter pre-step,
- * damped velocity integration, warm start, 10 sequential-impulse iterations) from knowledge of its source;
- * it cannot be checked against the real library offline.  External pins that ARE checked
- * (tests/test_oracle_v1.py): episode length 300 (gym_futbol/envs_v1/2v2/logs/evaluations.npz), observation
- * and action shapes (saved-model JSON), kick-off formations (closed form of team.py:52-112), single-body
- * closed forms (impulse -> delta v, damping 0.95^dt, speed clamps), two-body restitution 0.04.
+ * TEST INFRASTRUCTURE (see oracle/README.md).
+ * PINNED, game logic: tests/golden/v1_golden.npz holds traces of the reference's OWN, UNMODIFIED Python
+ * (envs_v1/futbol_env.py, team.py, player.py, ball.py) executed by oracle/ref_harness_v1.py with the Philox
+ * streams below injected; tests/test_oracle_v1_golden.py holds this file to them bit for bit (arith = 1).
+ * PARITY UNPINNED, physics: pymunk/Chipmunk is a third-party dependency that is neither vendored in
+ * /root/reference nor installable here, so those traces ran over oracle/pymunk_standin.py, a second, independent
+ * restatement of the same specification, not over the real library.  The physics below
+ * restates Chipmunk's published algorithm (cpSpaceStep: position integration, circle/circle and circle/segment
+ * narrow phase, arbiter pre-step, damped velocity integration, warm start, 10 sequential-impulse iterations)
+ * from knowledge of its source.  External pins that are also checked (tests/test_oracle_v1.py): episode length
+ * 300 (gym_futbol/envs_v1/2v2/logs/evaluations.npz), observation and action shapes (saved-model JSON), kick-off
+ * formations (closed form of team.py:52-112), single-body closed forms (impulse -> delta v, damping 0.95^dt,
+ * speed clamps), two-body restitution 0.04.
  *
  * What is specified here because Chipmunk leaves it implementation-defined:
  *   - body order: team A players 0..N-1, team B players N..2N-1, ball 2N (the order they are added to
@@ -21,16 +25,27 @@
  *     (:184-224: six boundary segments, then six goal-box segments);
  *   - the rotational terms of k_scalar vanish (contact offsets are parallel to the normal), friction is
  *     0 (mu_a * mu_b, circles have friction 0), so bodies never spin and tangential impulses are 0;
+ *   - cached impulses (cpArbiterUpdate / cpArbiterApplyCachedImpulse): a pair that touches again within the
+ *     3-step persistence window inherits its accumulated normal impulse jnAcc (the contact hashes of circle
+ *     pairs are all 0), but the warm-start impulse itself is applied only if the pair also touched in the
+ *     PREVIOUS space step: a cached arbiter that separated for one or two steps comes back in state
+ *     FIRST_COLLISION, for which cpArbiterApplyCachedImpulse returns early;
  *   - dt_coef of the warm start is 1: the only step with another dt is the 1e-4 step after a kick-off
- *     (:142), and no pair that was touching before a kick-off can touch again within the 3-step
- *     persistence window (all bodies are teleported to the formation);
+ *     (:142); nothing touches in it (all bodies are teleported to the formation), so no pair is warm-started
+ *     in it or in the step after it;
+ *   - cpSpace defaults as cpSpace.c writes them, in C float literals: collision_slop = 0.1f,
+ *     collision_bias = pow(1.0f - 0.1f, 60.0f) (both exact in double: 0x1.99999ap-4, 0x1.ccccccp-1);
  *   - a segment's closest point is taken by clamping the centre's coordinate (all segments are axis-aligned),
  *     and at most V1_MAX_CONTACTS = 32 contacts are solved per space step (pairs beyond that, in pair order,
  *     are ignored and counted in `overflow`; never reached in any test or bench run);
  *   - contact-point distance dist = (p2 - p1) . n with p1 = c_a + n r_a, p2 = c_b - n r_b (closest - n r_s
  *     for a segment), i.e. Chipmunk's (r2 - r1 + body_delta) . n without the round trip through r1, r2.
- * Arithmetic: one IEEE double operation per written operation, no contraction (-ffp-contract=off); x**2 is
- * x*x.  The CUDA kernel performs the same operations in the same order, so the two agree bit for bit.
+ * Arithmetic: one IEEE double operation per written operation, no contraction (-ffp-contract=off).  Two modes
+ * (as futbol_v0_oracle.c): arith = 0 "kernel": x**2 is x*x everywhere -- what the CUDA kernel computes, so the
+ * two agree bit for bit; arith = 1 "libm": the Python-level squares of the reference -- get_vec (:57),
+ * _ball_to_team_distance_arr (:490) and pymunk's Vec2d.length in the speed clamps (player.py:47, ball.py:51) --
+ * are libm pow(x, 2.0) as CPython's float ** computes them: bit-identical to the Python run on the same libm.
+ * The squares inside Chipmunk (C: cpvlengthsq, cpvdot) are products in both modes.
  *
  * Randomness (specification: oracle/philox.py; the reference is unseeded):
  *   stream 2, step t: right-team actions, player p: arrow = word(2p)*5 >> 32, key = word(2p+1)*5 >> 32 (:429)
@@ -78,7 +93,9 @@ typedef struct {
     int32_t n_players;     /* number_of_player, :65 */
     int32_t ep_limit;      /* first k with k additions of 0.1 > total_time (300 for 30) */
     double damping_dt;     /* pow(0.95, 0.1): space.damping ** dt, :99 */
-    double bias_coef;      /* 1 - pow(pow(0.9, 60), 0.1): Chipmunk collision_bias default */
+    double bias_coef;      /* 1 - pow(pow(1.0f - 0.1f, 60), 0.1): Chipmunk collision_bias default */
+    double slop;           /* 0.1f: Chipmunk collision_slop default */
+    int32_t arith, pad_;   /* 1 = libm pow for the Python-level squares, 0 = kernel arithmetic (x*x) */
     double form_x[2 * V1_MAX_N], form_y[2 * V1_MAX_N];   /* kick-off formation, team.py:52-112 */
 } OracleV1Config;
 
@@ -138,7 +155,11 @@ static void formation(int n, int right, double *xs, double *ys)
     }
 }
 
-int futbol_v1_oracle_config(OracleV1Config *cfg, uint64_t seed, int n_players, double total_time)
+/* gcc folds pow(x, 2.0) into x*x; the volatile pointer (and -fno-builtin-pow) keeps the libm call */
+static double (*volatile libm_pow_v1)(double, double) = pow;
+static double sq(const OracleV1Config *c, double x) { return c->arith ? libm_pow_v1(x, 2.0) : x * x; }
+
+int futbol_v1_oracle_config(OracleV1Config *cfg, uint64_t seed, int n_players, double total_time, int arith)
 {
     if (n_players < 1 || n_players > V1_MAX_N) return -1;
     memset(cfg, 0, sizeof(*cfg));
@@ -148,8 +169,10 @@ int futbol_v1_oracle_config(OracleV1Config *cfg, uint64_t seed, int n_players, d
     int k = 0;
     do { t += TIME_STEP; ++k; } while (!(t > total_time) && k < (1 << 30));
     cfg->ep_limit = k;
-    cfg->damping_dt = pow(0.95, TIME_STEP);
-    cfg->bias_coef = 1.0 - pow(pow(1.0 - 0.1, 60.0), TIME_STEP);
+    cfg->damping_dt = libm_pow_v1(0.95, TIME_STEP);
+    cfg->slop = (double)0.1f;
+    cfg->bias_coef = 1.0 - libm_pow_v1(libm_pow_v1((double)(1.0f - 0.1f), 60.0), TIME_STEP);
+    cfg->arith = arith ? 1 : 0;
     formation(n_players, 0, cfg->form_x, cfg->form_y);
     formation(n_players, 1, cfg->form_x + n_players, cfg->form_y + n_players);
     return 0;
@@ -273,7 +296,7 @@ static void process_action(const OracleV1Config *c, OracleV1Env *e, int p, int a
             if (key == 2) { gx = side == 0 ? WIDTH : 0.0; gy = HEIGHT / 2; force = BALL_FORCE_LIMIT; div = 2.0; }
             else { int t = pass_target(c, e, p, arrow); gx = e->p[t][0]; gy = e->p[t][1]; force = BALL_FORCE_LIMIT - 20; div = 10.0; }
             double vx = gx - e->p[ball][0], vy = gy - e->p[ball][1];
-            double mag = sqrt(vx * vx + vy * vy);
+            double mag = sqrt(sq(c, vx) + sq(c, vy));                /* get_vec, :55-58 */
             double bfx = force * vx / mag, bfy = force * vy / mag;
             e->v[ball][0] = e->v[ball][0] / div; e->v[ball][1] = e->v[ball][1] / div;
             e->owner_side = side;
@@ -283,7 +306,7 @@ static void process_action(const OracleV1Config *c, OracleV1Env *e, int p, int a
     } else if (key == 3) {                                       /* press :371-391 */
         if (!touching(e, p, ball) && arrow == 0) {
             double vx = e->p[ball][0] - e->p[p][0], vy = e->p[ball][1] - e->p[p][1];
-            double mag = sqrt(vx * vx + vy * vy);
+            double mag = sqrt(sq(c, vx) + sq(c, vy));
             double pfx = PLAYER_FORCE_LIMIT * vx / mag, pfy = PLAYER_FORCE_LIMIT * vy / mag;
             e->v[p][0] = e->v[p][0] + pfx * m_inv_p;
             e->v[p][1] = e->v[p][1] + pfy * m_inv_p;
@@ -292,7 +315,7 @@ static void process_action(const OracleV1Config *c, OracleV1Env *e, int p, int a
 }
 
 /* ---- Chipmunk subset ----------------------------------------------------------------------------- */
-typedef struct { int a, b, q; double nx, ny, n_mass, bias, bounce, jn, jbias; } Contact;
+typedef struct { int a, b, q, warm; double nx, ny, n_mass, bias, bounce, jn, jbias; } Contact;
 
 static double radius_of(int i, int ball) { return i == ball ? R_BALL : R_PLAYER; }
 static double minv_of(int i, int ball) { return i == ball ? 1.0 / BALL_WEIGHT : 1.0 / PLAYER_WEIGHT; }
@@ -319,7 +342,7 @@ static int ball_touches_segment(const OracleV1Env *e, int ball, int s)
 static void space_step(const OracleV1Config *c, OracleV1Env *e)
 {
     const int N = c->n_players, B = 2 * N + 1, ball = 2 * N, CC = B * (B - 1) / 2;
-    const double dt = TIME_STEP, slop = 0.1;
+    const double dt = TIME_STEP, slop = c->slop;
     Contact con[V1_MAX_CONTACTS];
     int nc = 0;
     /* 1. integrate positions (cpBodyUpdatePosition): p += (v + v_bias) dt; v_bias = 0 */
@@ -362,19 +385,21 @@ static void space_step(const OracleV1Config *c, OracleV1Env *e)
         double el = b >= 0 ? ELASTICITY * ELASTICITY : ELASTICITY * 0.0;
         k->bounce = ((vbx - e->v[a][0]) * k->nx + (vby - e->v[a][1]) * k->ny) * el;
         k->jn = e->age[q] <= 2 ? e->jn[q] : 0.0;                 /* cached arbiter: collision_persistence = 3 */
+        k->warm = e->age[q] == 0;                                /* state NORMAL: the pair touched in the previous step too */
         e->age[q] = 0;
     }
     e->contacts = nc;
     /* 6. integrate velocities through velocity_func (player.py:45-50, ball.py:49-54) */
     for (int i = 0; i < B; ++i) {
         double vx = e->v[i][0] * c->damping_dt + 0.0, vy = e->v[i][1] * c->damping_dt + 0.0;
-        double l = sqrt(vx * vx + vy * vy), mx = i == ball ? BALL_MAX_VELOCITY : PLAYER_MAX_VELOCITY;
+        double l = sqrt(sq(c, vx) + sq(c, vy)), mx = i == ball ? BALL_MAX_VELOCITY : PLAYER_MAX_VELOCITY;
         if (l > mx) { double sc = mx / l; vx = vx * sc; vy = vy * sc; }
         e->v[i][0] = vx; e->v[i][1] = vy;
     }
-    /* 7. warm start (cpArbiterApplyCachedImpulse, dt_coef = 1) */
+    /* 7. warm start (cpArbiterApplyCachedImpulse, dt_coef = 1; returns early for first-contact arbiters) */
     for (int i = 0; i < nc; ++i) {
         Contact *k = &con[i];
+        if (!k->warm) continue;
         double jx = k->nx * k->jn, jy = k->ny * k->jn, ma = minv_of(k->a, ball);
         e->v[k->a][0] = e->v[k->a][0] - jx * ma; e->v[k->a][1] = e->v[k->a][1] - jy * ma;
         if (k->b >= 0) { double mb = minv_of(k->b, ball); e->v[k->b][0] = e->v[k->b][0] + jx * mb; e->v[k->b][1] = e->v[k->b][1] + jy * mb; }
@@ -421,7 +446,7 @@ int futbol_v1_oracle_step_vs(const OracleV1Config *c, OracleV1Env *e, const uint
     e->step_draws = 0;
     e->flags = 0;
     double init_d[V1_MAX_N];                                      /* :433 */
-    for (int i = 0; i < N; ++i) { double dx = e->p[i][0] - e->p[ball][0], dy = e->p[i][1] - e->p[ball][1]; init_d[i] = sqrt(dx * dx + dy * dy); }
+    for (int i = 0; i < N; ++i) { double dx = e->p[i][0] - e->p[ball][0], dy = e->p[i][1] - e->p[ball][1]; init_d[i] = sqrt(sq(c, dx) + sq(c, dy)); }
     double bix = e->p[ball][0], biy = e->p[ball][1];              /* :435 */
     double reward = 0.0;
 
@@ -453,12 +478,12 @@ int futbol_v1_oracle_step_vs(const OracleV1Config *c, OracleV1Env *e, const uint
         int first = 1;
         for (int i = (N == 5 ? 3 : 0); i < N; ++i) {              /* :501-504 */
             double dx = e->p[i][0] - e->p[ball][0], dy = e->p[i][1] - e->p[ball][1];
-            double diff = init_d[i] - sqrt(dx * dx + dy * dy);
+            double diff = init_d[i] - sqrt(sq(c, dx) + sq(c, dy));
             if (first || diff > best) { best = diff; first = 0; }
         }
         reward = reward + best * 10;
         double ax = e->p[ball][0] - WIDTH, ay = e->p[ball][1] - HEIGHT / 2, ix = bix - WIDTH, iy = biy - HEIGHT / 2;
-        reward = reward + (sqrt(ix * ix + iy * iy) - sqrt(ax * ax + ay * ay)) * 10;
+        reward = reward + (sqrt(sq(c, ix) + sq(c, iy)) - sqrt(sq(c, ax) + sq(c, ay))) * 10;
     }
 
     int goal = 0;                                                 /* ball_contact_goal, :291-296 */

@@ -73,12 +73,19 @@ def _install_stubs():
 
         class MultiDiscrete(_Space):
             def __init__(self, nvec):
-                super().__init__(nvec=_np.asarray(nvec))
+                super().__init__(nvec=_np.asarray(nvec), sampler=None)
+
+            def sample(self):        # envs_v1/futbol_env.py:307; the v1 harness installs the draw stream here
+                if self.sampler is None:
+                    raise RuntimeError("gym stand-in: MultiDiscrete.sample() needs an injected sampler")
+                return self.sampler()
 
         spaces = types.ModuleType("gym.spaces")
         spaces.Discrete, spaces.Box, spaces.Tuple, spaces.MultiDiscrete = Discrete, Box, Tuple, MultiDiscrete
         error = types.ModuleType("gym.error")
         utils = types.ModuleType("gym.utils")
+        seeding = types.ModuleType("gym.utils.seeding")          # envs_v1/futbol_env.py:3 imports it, never uses it
+        utils.seeding = seeding
         envs = types.ModuleType("gym.envs")
         registration = types.ModuleType("gym.envs.registration")
         registration.registry = {}
@@ -89,7 +96,7 @@ def _install_stubs():
         registration.register = register
         envs.registration = registration
         gym.Env, gym.spaces, gym.error, gym.utils, gym.envs = Env, spaces, error, utils, envs
-        sys.modules.update({"gym": gym, "gym.spaces": spaces, "gym.error": error, "gym.utils": utils,
+        sys.modules.update({"gym": gym, "gym.spaces": spaces, "gym.error": error, "gym.utils": utils, "gym.utils.seeding": seeding,
                             "gym.envs": envs, "gym.envs.registration": registration})
     if "matplotlib" not in sys.modules:
         mpl = types.ModuleType("matplotlib")

@@ -14,7 +14,7 @@ NSEG = 12
 MAX_PAIRS = MAX_BODIES * (MAX_BODIES - 1) // 2 + MAX_BODIES * NSEG
 
 CFG_DTYPE = np.dtype([("seed", np.uint64), ("n_players", np.int32), ("ep_limit", np.int32), ("damping_dt", np.float64),
-                      ("bias_coef", np.float64), ("form_x", np.float64, (2 * MAX_N,)), ("form_y", np.float64, (2 * MAX_N,))],
+                      ("bias_coef", np.float64), ("slop", np.float64), ("arith", np.int32), ("pad_", np.int32), ("form_x", np.float64, (2 * MAX_N,)), ("form_y", np.float64, (2 * MAX_N,))],
                      align=True)
 ENV_DTYPE = np.dtype([("p", np.float64, (MAX_BODIES, 2)), ("v", np.float64, (MAX_BODIES, 2)), ("vb", np.float64, (MAX_BODIES, 2)),
                       ("jn", np.float64, (MAX_PAIRS,)), ("age", np.uint8, (MAX_PAIRS,)), ("t_total", np.uint64),
@@ -35,7 +35,7 @@ def lib():
         assert L.futbol_v1_oracle_env_bytes() == ENV_DTYPE.itemsize, (L.futbol_v1_oracle_env_bytes(), ENV_DTYPE.itemsize)
         assert L.futbol_v1_oracle_cfg_bytes() == CFG_DTYPE.itemsize
         L.futbol_v1_oracle_config.restype = C.c_int
-        L.futbol_v1_oracle_config.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_double]
+        L.futbol_v1_oracle_config.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_double, C.c_int]
         L.futbol_v1_oracle_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.futbol_v1_oracle_reset.argtypes = [C.c_void_p, C.c_void_p]
         L.futbol_v1_oracle_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -55,12 +55,12 @@ def _ptr(a):
 class OracleV1:
     """A batch of v1 oracle envs with global ids env_id0 .. env_id0+n-1 (constructed and reset, like Futbol())."""
 
-    def __init__(self, n=1, seed=0, env_id0=0, number_of_player=2, total_time=30.0):
+    def __init__(self, n=1, seed=0, env_id0=0, number_of_player=2, total_time=30.0, arith=0):
         self.lib = lib()
         self.n, self.N = int(n), int(number_of_player)
         self.obs_dim = 4 + 8 * self.N
         self.cfg = np.zeros(1, dtype=CFG_DTYPE)
-        if self.lib.futbol_v1_oracle_config(_ptr(self.cfg), int(seed), self.N, float(total_time)) != 0:
+        if self.lib.futbol_v1_oracle_config(_ptr(self.cfg), int(seed), self.N, float(total_time), int(arith)) != 0:
             raise ValueError("number_of_player must be 1..10")
         self.envs = np.zeros(self.n, dtype=ENV_DTYPE)
         for i in range(self.n):

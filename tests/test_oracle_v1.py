@@ -112,15 +112,18 @@ def test_two_body_restitution():
 def test_wall_contact_keeps_a_pushing_player_in():
     """A player dashing into the bottom wall: every step the position integrates the fresh 2.0 of velocity
     (0.2 inwards) before the solve, and the bias impulse removes bias_coef * (penetration - slop); the
-    penetration therefore settles at slop + 0.2 / bias_coef, bias_coef = 1 - 0.9**6 (Chipmunk's defaults)."""
+    penetration therefore settles at slop + 0.2 / bias_coef, bias_coef = 1 - 0.9f**6 and slop = 0.1f (Chipmunk's
+    defaults, written as C float literals in cpSpace.c)."""
     o = OracleV1(1, number_of_player=1)
     e = o.envs[0]
     e["p"][0] = (30.0, 6.0)
     for _ in range(60):
         o.step_one(0, [3, 1])
-    bias_coef = 1.0 - (0.9 ** 60) ** 0.1
-    assert abs(float(o.cfg["bias_coef"][0]) - bias_coef) < 1e-15
-    assert abs((2.5 - e["p"][0, 1]) - (0.1 + 0.2 / bias_coef)) < 1e-6     # r_player + r_segment = 2.5 above y = 0
+    f09, slop = float(np.float32(1.0) - np.float32(0.1)), float(np.float32(0.1))
+    assert f09.hex() == "0x1.ccccccp-1".replace("p", "0000000p") and slop.hex() == "0x1.99999a0000000p-4"
+    bias_coef = 1.0 - (f09 ** 60) ** 0.1
+    assert abs(float(o.cfg["bias_coef"][0]) - bias_coef) < 1e-15 and float(o.cfg["slop"][0]) == slop
+    assert abs((2.5 - e["p"][0, 1]) - (slop + 0.2 / bias_coef)) < 1e-6     # r_player + r_segment = 2.5 above y = 0
     assert abs(e["v"][0, 1]) < 1e-9                                       # the normal velocity is removed every step
     q_wall = 3 * 2 // 2 + 0 * 12 + 5
     assert e["age"][q_wall] == 0 and e["jn"][q_wall] > 0.0

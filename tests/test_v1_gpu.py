@@ -1,6 +1,7 @@
 """GPU parity tests for the v1 path: the CUDA kernels (through the C ABI) against the v1 oracle on the same
-seeds and actions.  The oracle is this repository's own restatement (parity with pymunk is UNPINNED, see
-oracle/futbol_v1_oracle.c); the bar against it is bit-exact float64 and exact integers."""
+seeds and actions (bar: bit-exact float64 and exact integers), and against traces of the reference's own Python
+(tests/golden/v1_golden.npz).  The oracle is pinned to those traces bit for bit (tests/test_oracle_v1_golden.py); the
+physics under them is the pymunk stand-in, not the real library (rows b3 / b6 stay unpinned, oracle/futbol_v1_oracle.c)."""
 import numpy as np
 import pytest
 
@@ -159,3 +160,74 @@ def test_v1_and_v0_step_api_float32_outputs_ragged_batch(torch_cuda):
         obs, rew, done, _ = env0.step(torch_cuda.from_numpy(a0[t]).cuda())
         assert np.array_equal(obs.cpu().numpy(), want0["obs"][t].astype(np.float32))
         assert np.array_equal(rew.cpu().numpy(), want0["reward"][t].astype(np.float32)) and np.array_equal(done.cpu().numpy(), want0["done"][t])
+
+
+# ---- against the reference's own Python (tests/golden/v1_golden.npz, see tests/test_oracle_v1_golden.py) ----------------
+def _golden_v1_cases():
+    import json
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "v1_golden.npz"))
+    cases = {}
+    for key in z.files:
+        case, field = key.split("/")
+        cases.setdefault(case, {})[field] = z[key]
+    cases.pop("libm_fingerprint"), cases.pop("coverage")
+    for c in cases.values():
+        c["meta"] = json.loads(str(c["meta"]))
+    return cases
+
+
+def test_v1_golden_reference_traces(torch_cuda):
+    """The CUDA path against traces of the UNMODIFIED reference v1 Python (run over the pymunk stand-in): every integer
+    output of every step exact (done, goal / out-of-bounds / goal-side flags, possession side), observation and reward
+    within 1e-9 relative (the kernel squares with x*x, CPython's float ** calls libm pow); north_star allows 1e-4."""
+    from gym_futbol_b200 import FutbolV1VecEnv
+    worst, steps_checked = 0.0, 0
+    for name, c in _golden_v1_cases().items():
+        m = c["meta"]
+        N, T = m["number_of_player"], m["steps"]
+        env = FutbolV1VecEnv(1, number_of_player=N, seed=m["seed"], env_id_offset=m["env_id"], total_time=m["kwargs"].get("total_time", 30),
+                             dtype=torch_cuda.float64, auto_reset=False)
+        obs0 = env.reset().cpu().numpy()[0]
+        assert np.abs(obs0 - c["obs0"]).max() <= 1e-12, name
+        acts = torch_cuda.from_numpy(c["action"]).cuda().reshape(T, 1, 2 * N)
+        obs_l, rew_l, done_l, st_l = [], [], [], []
+        for t in range(T):
+            obs, rew, done, _ = env.step(acts[t])
+            obs_l.append(obs.clone()); rew_l.append(rew.clone()); done_l.append(done.clone())
+            st = env.get_state()[0]
+            st_l.append((int(st["flags"]), int(st["owner_side"])))
+            if int(st["flags"]) & 4:
+                env.reset()
+        obs = torch_cuda.stack(obs_l).cpu().numpy()[:, 0]
+        rew = torch_cuda.stack(rew_l).cpu().numpy()[:, 0]
+        done = torch_cuda.stack(done_l).cpu().numpy()[:, 0]
+        assert np.array_equal(done, c["done"]), name
+        assert np.array_equal(np.array([s[0] for s in st_l], np.uint8), c["flags"]), name
+        assert np.array_equal(np.array([s[1] for s in st_l], np.uint8), c["owner_side"]), name
+        for a, b in ((obs, c["obs"]), (rew, c["reward"])):
+            worst = max(worst, float((np.abs(a - b) / np.maximum(1.0, np.abs(b))).max()))
+        steps_checked += T
+    assert worst <= 1e-9 and steps_checked >= 15000
+    print("v1 golden: %d reference steps, max relative float error %.2e" % (steps_checked, worst))
+
+
+def test_v1_golden_batch_members(torch_cuda):
+    """'Env #k inside a batch': the eight batch_* golden envs (global ids 2000..2007) stepped as members of one batch, fused
+    rollout with given actions: fp32 streams equal the reference's doubles to fp32 resolution, dones exact."""
+    from gym_futbol_b200 import FutbolV1VecEnv
+    cases = _golden_v1_cases()
+    for N in (2, 5):
+        members = [cases["batch_n%d_s3_e%d" % (N, e)] for e in range(2000, 2008)]
+        T = members[0]["meta"]["steps"]
+        env = FutbolV1VecEnv(40, number_of_player=N, seed=3, env_id_offset=1990)      # ids 1990..2029: members at 10..17
+        env.reset()
+        acts = np.zeros((T, 40, 2 * N), np.uint8)
+        for k, c in enumerate(members):
+            acts[:, 10 + k] = c["action"]
+        obs, rew, done = env.rollout(T, actions=torch_cuda.from_numpy(acts).cuda())
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        for k, c in enumerate(members):
+            assert np.array_equal(done[:, 10 + k], c["done"])
+            assert (np.abs(obs[:, 10 + k] - c["obs"]) <= 2e-7 * np.maximum(1.0, np.abs(c["obs"]))).all()
+            assert (np.abs(rew[:, 10 + k] - c["reward"]) <= 2e-7 * np.maximum(1.0, np.abs(c["reward"]))).all()
