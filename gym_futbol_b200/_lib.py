@@ -12,7 +12,7 @@ import numpy as np
 
 from . import build as _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 VARIANT_V0, VARIANT_V1 = 0, 1
 
 
@@ -35,7 +35,18 @@ V0_ENV_STATE = np.dtype([("rows", np.float64, (5, 5)), ("t_total", np.uint64), (
                          ("ai_score", np.int32), ("opp_score", np.int32), ("owner", np.uint8),
                          ("last_owner", np.uint8), ("flags", np.uint8), ("pad_", np.uint8)], align=True)
 V1_ENV_STATE = np.dtype([("body", np.float64, (21, 6)), ("t_total", np.uint64), ("stamp", np.uint32), ("ep_step", np.int32),
-                         ("owner_side", np.uint8), ("flags", np.uint8), ("pad_", np.uint8, (2,))], align=True)
+                         ("owner_side", np.uint8), ("flags", np.uint8), ("pad_", np.uint8, (6,))], align=True)   # the header
+
+
+def v1_env_state_dtype(n_players):
+    """numpy mirror of one whole v1 record: the FutbolV1EnvState header + the env's arbiter cache (jn[P], last[P])."""
+    B = 2 * int(n_players) + 1
+    P = B * (B - 1) // 2 + 12 * B
+    fields = [(name, V1_ENV_STATE.fields[name][0]) for name in V1_ENV_STATE.names]
+    fields += [("jn", np.float64, (P,)), ("last", np.uint32, (P,))]
+    if P & 1:
+        fields.append(("pad2_", np.uint32))
+    return np.dtype(fields, align=True)
 STATS_DTYPE = np.dtype([("reward_sum", np.float64), ("env_steps", np.uint64), ("episodes", np.uint64),
                         ("goals_ai", np.uint64), ("goals_opp", np.uint64), ("out_of_field", np.uint64),
                         ("reserved", np.uint64, (2,))])
@@ -75,6 +86,9 @@ def load():
             if not os.path.exists(path):
                 raise FutbolError("libfutbol_b200.so is not built and cannot be built here (%s); "
                                   "there is no CPU fallback" % exc) from exc
+            import warnings
+            warnings.warn("libfutbol_b200.so is OLDER than its sources and could not be rebuilt (%s): loading the stale "
+                          "library; only its ABI version is checked" % (str(exc).splitlines()[0],), RuntimeWarning, stacklevel=2)
     L = C.CDLL(path)
     vp = C.c_void_p
     L.futbol_create.restype = C.c_int

@@ -38,16 +38,37 @@ def is_stale():
 
 
 def build_extension(force=False, verbose=False, extra_flags=(), out=None):
-    """`extra_flags` / `out`: tuning variants (e.g. -DFUTBOL_MIN_BLOCKS=4 into libfutbol_b200_mb4.so)."""
+    """`extra_flags` / `out`: tuning variants (e.g. -DFUTBOL_MIN_BLOCKS=4 into libfutbol_b200_mb4.so).
+
+    Safe when several processes call it at once (every rank of a torchrun job after a fresh clone): the build runs
+    under an exclusive file lock, nvcc writes to a temporary name in the same directory and the finished library is
+    moved into place atomically, so no process can dlopen a half-written file; a process that waited on the lock
+    finds the library fresh and does not rebuild.
+    """
     if out is None and not force and not is_stale():
         return LIB
+    default_target = out is None
     out = LIB if out is None else os.path.join(CSRC, out)
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + list(SOURCES)
-    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
-    if verbose:
-        sys.stderr.write(proc.stderr)
+    import fcntl
+    with open(out + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if default_target and not force and not is_stale():      # built by another process while we waited
+                return out
+            tmp = "%s.tmp.%d" % (out, os.getpid())
+            cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + list(SOURCES)
+            try:
+                proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+                if proc.returncode != 0:
+                    raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))
+                os.replace(tmp, out)
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+            if verbose:
+                sys.stderr.write(proc.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return out
 
 

@@ -134,6 +134,8 @@ int futbol_create(const FutbolConfig *cfg, FutbolHandle **out)
         // values (tests/test_oracle_v1_golden.py checks them against math.pow and the oracle's configuration).
         Q.damping_dt = 0x1.fd6168eb56e59p-1;     // pow(0.95, 0.1): space.damping ** TIME_STEP (:99)
         Q.bias_coef = 0x1.dfcdf3e02c8a4p-2;      // 1 - pow(pow(1.0f - 0.1f, 60.0f), 0.1): cpSpace.c's default collision_bias
+        Q.clamp_sq_player = sqrt_less_than_bound(nextafter(v1::kPlayerMaxV, INFINITY));   // sqrt(s) > 10  <=>  s > bound
+        Q.clamp_sq_ball = sqrt_less_than_bound(nextafter(v1::kBallMaxV, INFINITY));
         formation_v1(cfg->n_players, false, Q.form_x, Q.form_y);
         formation_v1(cfg->n_players, true, Q.form_x + cfg->n_players, Q.form_y + cfg->n_players);
     }
@@ -165,7 +167,7 @@ size_t futbol_state_bytes(const FutbolHandle *h)
     if (!h) return 0;
     return h->is_v1 ? v1::state_bytes(h->cfg.n_envs, h->cfg.n_players) : v0_state_bytes(h->cfg.n_envs);
 }
-size_t futbol_env_state_bytes(const FutbolHandle *h) { return h ? (h->is_v1 ? sizeof(FutbolV1EnvState) : sizeof(FutbolV0EnvState)) : 0; }
+size_t futbol_env_state_bytes(const FutbolHandle *h) { return h ? (h->is_v1 ? v1::env_state_bytes(h->cfg.n_players) : sizeof(FutbolV0EnvState)) : 0; }
 int futbol_obs_dim(const FutbolHandle *h) { return h ? (h->is_v1 ? v1::obs_dim(h->cfg.n_players) : 30) : 0; }
 int futbol_act_dim(const FutbolHandle *h) { return h ? (h->is_v1 ? 2 * h->cfg.n_players : 1) : 0; }
 int futbol_draw_limit_steps(const FutbolHandle *h) { return h ? (h->is_v1 ? h->v1.ep_limit : h->v0.ep_limit + 1) : 0; }
@@ -266,8 +268,8 @@ int futbol_get_state(FutbolHandle *h, const void *state, void *aos_out, void *st
 int futbol_set_state(FutbolHandle *h, void *state, const void *aos_in, void *stream)
 {
     if (h == nullptr || state == nullptr || aos_in == nullptr) return fail(FUTBOL_ERR_ARG, "null argument%s");
-    if (h->is_v1) return fail(FUTBOL_ERR_UNSUPPORTED, "futbol_set_state is not available for the v1 variant%s");
-    cudaError_t e = v0_launch_set_state(h->cfg.n_envs, state, aos_in, (cudaStream_t)stream);
+    cudaError_t e = h->is_v1 ? v1::launch_set_state(h->cfg.n_envs, h->cfg.n_players, state, aos_in, (cudaStream_t)stream)
+                             : v0_launch_set_state(h->cfg.n_envs, state, aos_in, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     h->initialised = true;
     h->launches += 1;

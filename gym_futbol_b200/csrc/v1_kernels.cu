@@ -4,8 +4,8 @@
 // B = 2N + 1 bodies, P = B(B-1)/2 + 12 B shape pairs:
 //   double  body[6 B][np]   per body x, y, vx, vy, v_bias_x, v_bias_y (team A, team B, ball)
 //   uint64  t_total[np];  uint32 stamp[np];  int32 ep_step[np];  uint8 owner_side[np], flags[np]
-//   double  jn[P][np];  uint32 last[P][np]    the arbiter cache: accumulated normal impulse and the stamp of
-//                                             the space step in which the pair last touched
+//   CacheRec cache[P][np]                     the arbiter cache, 16 bytes per shape pair: accumulated normal impulse and
+//                                             the stamp of the space step in which the pair last touched
 // Inside a kernel the 6 B doubles sit in shared memory (one column per lane), scalars in registers; the
 // arbiter cache stays in HBM and is touched only by pairs in contact.
 #include <cuda_runtime.h>
@@ -18,7 +18,7 @@ namespace futbol {
 namespace v1 {
 
 struct StateView {
-    double *body; uint64_t *t_total; uint32_t *stamp; int32_t *ep_step; uint8_t *owner_side, *flags; double *jn; uint32_t *last;
+    double *body; uint64_t *t_total; uint32_t *stamp; int32_t *ep_step; uint8_t *owner_side, *flags; CacheRec *cache;
     size_t np;
 };
 
@@ -27,7 +27,7 @@ __host__ __device__ inline size_t padded(int n) { return ((size_t)n + 255) & ~(s
 size_t state_bytes(int n_envs, int n_players)
 {
     const size_t B = 2 * n_players + 1, P = n_pairs((int)B);
-    return padded(n_envs) * (6 * B * 8 + 8 + 4 + 4 + 1 + 1 + P * 12);
+    return padded(n_envs) * (6 * B * 8 + 8 + 4 + 4 + 1 + 1 + P * sizeof(CacheRec));
 }
 
 __host__ __device__ inline StateView make_view(void *base, int n, int n_players)
@@ -37,9 +37,8 @@ __host__ __device__ inline StateView make_view(void *base, int n, int n_players)
     v.np = padded(n);
     char *p = (char *)base;
     v.body = (double *)p;        p += v.np * 6 * B * 8;
-    v.jn = (double *)p;          p += v.np * P * 8;
+    v.cache = (CacheRec *)p;     p += v.np * P * sizeof(CacheRec);
     v.t_total = (uint64_t *)p;   p += v.np * 8;
-    v.last = (uint32_t *)p;      p += v.np * P * 4;
     v.stamp = (uint32_t *)p;     p += v.np * 4;
     v.ep_step = (int32_t *)p;    p += v.np * 4;
     v.owner_side = (uint8_t *)p; p += v.np;
@@ -141,7 +140,7 @@ __global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, 
     const uint32_t env_id = P.env_id_offset + (uint32_t)i;
     V1Regs s;
     if (live) {
-        const PairCache C{v.jn + i, v.last + i, v.np};
+        const PairCache C{v.cache + i, v.np};
         Contact con[kMaxContacts];
         load_state(v, i, L, s, B);
         const StepResult r = v1_step<REGC>(L, s, P, env_id, actions + (size_t)i * 2 * N, C, con, form_base,
@@ -179,7 +178,7 @@ __global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t 
     const Lane L = make_lane(warp, lane, N);
     // padding lanes of the last warp step env 0's cache column?  No: they get a private dummy state and never touch HBM
     const int ci = live ? i : 0;
-    const PairCache C{v.jn + ci, v.last + ci, v.np};
+    const PairCache C{v.cache + ci, v.np};
     Contact con[kMaxContacts];
 
     V1Regs s;
@@ -239,21 +238,53 @@ __global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t 
     }
 }
 
-__global__ void v1_get_state_kernel(int n, int n_players, StateView v, FutbolV1EnvState *out)
+// AoS record = FutbolV1EnvState header + double jn[P] + uint32 last[P], padded to 8 bytes (include/futbol_b200.h)
+__host__ __device__ inline size_t record_bytes(int n_players)
+{
+    const size_t P = n_pairs(2 * n_players + 1);
+    return (sizeof(FutbolV1EnvState) + P * 12 + 7) & ~(size_t)7;
+}
+size_t env_state_bytes(int n_players) { return record_bytes(n_players); }
+
+__global__ void v1_get_state_kernel(int n, int n_players, StateView v, unsigned char *out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int B = 2 * n_players + 1;
-    FutbolV1EnvState *e = out + i;                    // written field by field: the record is 1 KB
+    const int B = 2 * n_players + 1, P = n_pairs(B);
+    FutbolV1EnvState *e = reinterpret_cast<FutbolV1EnvState *>(out + (size_t)i * record_bytes(n_players));   // written field by field
     for (int b = 0; b < 21; ++b)
         for (int f = 0; f < 6; ++f) e->body[b][f] = b < B ? v.body[(size_t)(6 * b + f) * v.np + i] : 0.0;
     e->t_total = v.t_total[i]; e->stamp = v.stamp[i]; e->ep_step = v.ep_step[i]; e->owner_side = v.owner_side[i];
-    e->flags = v.flags[i]; e->pad_[0] = e->pad_[1] = 0;
+    e->flags = v.flags[i];
+    for (int k = 0; k < 6; ++k) e->pad_[k] = 0;
+    double *jn = reinterpret_cast<double *>(e + 1);
+    uint32_t *last = reinterpret_cast<uint32_t *>(jn + P);
+    for (int q = 0; q < P; ++q) { const CacheRec r = v.cache[(size_t)q * v.np + i]; jn[q] = r.jn; last[q] = r.last; }
+    if (P & 1) last[P] = 0;
+}
+
+__global__ void v1_set_state_kernel(int n, int n_players, StateView v, const unsigned char *in)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int B = 2 * n_players + 1, P = n_pairs(B);
+    const FutbolV1EnvState *e = reinterpret_cast<const FutbolV1EnvState *>(in + (size_t)i * record_bytes(n_players));
+    for (int b = 0; b < B; ++b)
+        for (int f = 0; f < 6; ++f) v.body[(size_t)(6 * b + f) * v.np + i] = e->body[b][f];
+    v.t_total[i] = e->t_total; v.stamp[i] = e->stamp; v.ep_step[i] = e->ep_step; v.owner_side[i] = e->owner_side;
+    v.flags[i] = e->flags;
+    const double *jn = reinterpret_cast<const double *>(e + 1);
+    const uint32_t *last = reinterpret_cast<const uint32_t *>(jn + P);
+    for (int q = 0; q < P; ++q) { CacheRec r; r.jn = jn[q]; r.last = last[q]; r.pad_ = 0; v.cache[(size_t)q * v.np + i] = r; }
 }
 
 // ---- host launchers ------------------------------------------------------------------------------------
 static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
+#ifdef FUTBOL_V1_THREADS
+static inline int threads_for(int) { return FUTBOL_V1_THREADS; }   // tuning builds (tools/build_variant.py)
+#else
 static inline int threads_for(int n_players) { return n_players <= 5 ? 64 : 32; }   // keeps a block under 48 KB of shared memory (10v10: 33 KB per warp)
+#endif
 #ifdef FUTBOL_V1_REGC
 static inline int regc_for(int) { return FUTBOL_V1_REGC; }     // tuning builds (tools/build_variant.py)
 #else
@@ -267,9 +298,7 @@ cudaError_t launch_reset(const V1Params &P, void *state, const uint8_t *mask, vo
     const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
     if (init) {   // first construction: an empty arbiter cache
         const size_t P_ = n_pairs(2 * P.n_players + 1);
-        cudaError_t e = cudaMemsetAsync(v.jn, 0, v.np * P_ * 8, st);
-        if (e != cudaSuccess) return e;
-        e = cudaMemsetAsync(v.last, 0, v.np * P_ * 4, st);
+        cudaError_t e = cudaMemsetAsync(v.cache, 0, v.np * P_ * sizeof(CacheRec), st);
         if (e != cudaSuccess) return e;
     }
     if (obs_f64) v1_reset_kernel<double><<<blocks_for(P.n_envs, t), t, sm, st>>>(P, v, mask, (double *)obs, init);
@@ -305,7 +334,13 @@ cudaError_t launch_rollout(const V1Params &P, void *state, int K, const uint8_t 
 
 cudaError_t launch_get_state(int n, int n_players, const void *state, void *aos, cudaStream_t st)
 {
-    v1_get_state_kernel<<<blocks_for(n, 128), 128, 0, st>>>(n, n_players, make_view(const_cast<void *>(state), n, n_players), (FutbolV1EnvState *)aos);
+    v1_get_state_kernel<<<blocks_for(n, 128), 128, 0, st>>>(n, n_players, make_view(const_cast<void *>(state), n, n_players), (unsigned char *)aos);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_set_state(int n, int n_players, void *state, const void *aos, cudaStream_t st)
+{
+    v1_set_state_kernel<<<blocks_for(n, 128), 128, 0, st>>>(n, n_players, make_view(state, n, n_players), (const unsigned char *)aos);
     return cudaGetLastError();
 }
 

@@ -72,6 +72,7 @@ struct V1Params {
     int auto_reset;
     double damping_dt;    // pow(0.95, 0.1): space.damping ** dt, :99
     double bias_coef;     // 1 - pow(pow(1.0f - 0.1f, 60), 0.1): Chipmunk collision_bias default (float literals, cpSpace.c)
+    double clamp_sq_player, clamp_sq_ball;   // largest |v|^2 whose correctly rounded root is <= 10 / 25: `sqrt(s) > max` as `s > bound`
     double form_x[2 * kMaxN], form_y[2 * kMaxN];   // kick-off formation, team.py:52-112
 };
 
@@ -108,8 +109,31 @@ __device__ __forceinline__ Lane make_lane(int warp_in_block, int lane, int n_pla
     return L;
 }
 
-// the arbiter cache of this environment in HBM: pair q at jn[q * stride], last[q * stride]
-struct PairCache { double *jn; uint32_t *last; size_t stride; };
+// the arbiter cache of this environment in HBM: pair q at rec[q * stride], one 16-byte record per shape pair (the
+// accumulated normal impulse and the stamp of the space step in which the pair last touched), so that a touching pair
+// costs one 32-byte sector each way (as two arrays it cost two: ncu counted 1.17 x the algorithmic DRAM bytes at 5v5)
+struct __align__(16) CacheRec { double jn; uint32_t last, pad_; };
+struct PairCache { CacheRec *rec; size_t stride; };
+__device__ __forceinline__ CacheRec cache_load(const PairCache &C, int q)
+{
+#ifndef FUTBOL_HOST_SHIM
+    const double2 raw = *reinterpret_cast<const double2 *>(C.rec + (size_t)q * C.stride);      // one 128-bit load
+    CacheRec r;
+    r.jn = raw.x; r.last = (uint32_t)__double2loint(raw.y); r.pad_ = 0;
+    return r;
+#else
+    return C.rec[(size_t)q * C.stride];
+#endif
+}
+__device__ __forceinline__ void cache_store(const PairCache &C, int q, double jn, uint32_t stamp)
+{
+#ifndef FUTBOL_HOST_SHIM
+    *reinterpret_cast<double2 *>(C.rec + (size_t)q * C.stride) = make_double2(jn, __hiloint2double(0, (int)stamp));
+#else
+    CacheRec r; r.jn = jn; r.last = stamp; r.pad_ = 0;
+    C.rec[(size_t)q * C.stride] = r;
+#endif
+}
 
 // scalars (registers)
 struct V1Regs {
@@ -374,8 +398,8 @@ __device__ __forceinline__ void warm_start_contact(Lane L, const Contact &k, int
 }
 
 // cpSpaceStep(dt = 0.1).  Returns the number of contacts; `overflow` counts contacts beyond kMaxContacts.
-// The first two contacts of a step live in registers (c0, c1), the rest in the local-memory list `con` (index
-// i - 2): a step rarely has more than two, and the ten solver iterations would otherwise wait on local-memory
+// The first REGC contacts of a step live in registers (c0, c1, c2), the rest in the local-memory list `con` (index
+// i - REGC): a step rarely has more than two, and the ten solver iterations would otherwise wait on local-memory
 // loads (L1 is small next to 200 KB of shared memory: ncu showed 53 % of the long-scoreboard stalls there).
 // REGC = how many contacts are register-resident, chosen by measurement (end of round 1, env-steps/s): 0 for 1v1 (one
 // costs 2 %), 1 for N = 2, 3 (a second one costs occupancy: 2v2 -20 %), 2 for N = 4 ... 6, 3 for N >= 7 (+3 % at 7v7 and
@@ -397,109 +421,120 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
         L.f(o + kPY) = dadd(L.f(o + kPY), dmul(dadd(L.f(o + kVY), L.f(o + kBY)), kDt));
         L.f(o + kBX) = 0.0; L.f(o + kBY) = 0.0;
     }
-    // 2. narrow phase in pair-id order + 5. arbiter pre-step (uses the velocities before step 6)
+    // 2. narrow phase in pair-id order.
     //    pass 0: circle/circle pairs (i < j), id j(j-1)/2 + i: outer loop over j, inner over i;
     //    pass 1: circle/segment pairs, id CC + 12 * body + segment.
-    //    Candidates, visited in ascending index (= ascending pair id).  Pass 0: every body i < jb.  Pass 1: only the
-    //    segments that can be reached at all -- r + r_segment <= 2.5, the left-hand segments {0, 1, 6, 7, 8} lie at
-    //    x <= 0, the right-hand ones {3, 4, 9, 10, 11} at x >= 105, segment 5 on y = 0 and segment 2 on y = 68 --
-    //    so a body strictly inside the pitch tests none and a body at a touchline tests one.
-    //    The scan only RECORDS the touching pairs (11 bits each, up to four pending in a register); their contacts are
-    //    built afterwards, all lanes together.  Built inside the scan, the 90-instruction block ran once for every
-    //    pair that touched in ANY of the warp's 32 environments (about six times a step for 2v2, twenty for 5v5) with
-    //    one or two lanes active; now it runs as many times as the busiest environment has contacts.
+    //    The scan is the SAME instruction stream for every lane: for body j a branch-free loop over all i < j builds the
+    //    mask of touching partners (two shared-memory loads and six fp64 operations per pair, independent across
+    //    pairs, so they pipeline), and only a non-empty mask -- a few percent of the bodies -- enters the branch that
+    //    records the hits.  (The first version walked a per-lane candidate list through a resumable state machine: one
+    //    pair per loop trip, 14 to 24 of 32 lanes active, about 90 warp-instructions per pair -- a third of all
+    //    instructions of a 5v5 step and 44 % at 10v10, profiles/r2_v1_history.md.)
+    //    Segments: only those that can be reached at all are tested -- r + r_segment <= 2.5, the left-hand segments
+    //    {0, 1, 6, 7, 8} lie at x <= 0, the right-hand ones {3, 4, 9, 10, 11} at x >= 105, segment 5 on y = 0 and
+    //    segment 2 on y = 68 -- so a body strictly inside the pitch tests none.
+    //    A hit is RECORDED as an 11-bit code (in the q field of its future contact); the contacts are built afterwards,
+    //    all lanes together, so that the 90-instruction block runs as many times as the busiest environment has
+    //    contacts, not once per pair that touches in any of the warp's 32 environments.
     {
-        int pass = 0, jb = 1;
-        uint32_t cand = 1u;                                              // pass 0, jb = 1: body 0
-        double jx_ = L.f(kBodyStride + kPX), jy_ = L.f(kBodyStride + kPY);
-        bool scanning = true;
+        auto record = [&](uint32_t code) {
+            if (nc == kMaxContacts) { overflow += 1; return; }
+            if (REGC > 0 && nc == 0) c0.q = (int)code; else if (REGC > 1 && nc == 1) c1.q = (int)code; else if (REGC > 2 && nc == 2) c2.q = (int)code;
+            else con[nc - REGC].q = (int)code;
+            nc += 1;
+        };
+        constexpr double kPP2 = (kRPlayer + kRPlayer) * (kRPlayer + kRPlayer), kPB2 = (kRPlayer + kRBall) * (kRPlayer + kRBall);
 #pragma unroll 1
-        while (scanning) {
-            uint64_t hits = 0;
-            int nh = 0;
+        for (int jb = 1; jb < B; ++jb) {
+            const double jx = L.f(jb * kBodyStride + kPX), jy = L.f(jb * kBodyStride + kPY);
+            const double mind2 = jb == ball ? kPB2 : kPP2;               // a = ii < jb: only b can be the ball
+            uint32_t hj = 0u;
+#pragma unroll 4
+            for (int ii = 0; ii < jb; ++ii) {
+                const double dx = dsub(jx, L.f(ii * kBodyStride + kPX)), dy = dsub(jy, L.f(ii * kBodyStride + kPY));
+                const double distsq = dadd(dmul(dx, dx), dmul(dy, dy));
+                hj |= distsq < mind2 ? (1u << ii) : 0u;
+            }
+            while (hj != 0u) {
+                const int ii = __ffs((int)hj) - 1;
+                hj &= hj - 1u;
+                record(((uint32_t)jb << 1) | ((uint32_t)ii << 6));
+            }
+        }
 #pragma unroll 1
-            while (nh < 4) {
-                if (cand == 0u) {                                        // next body, next pass
-                    jb += 1;
-                    if (jb >= B) { if (pass == 1) { scanning = false; break; } pass = 1; jb = 0; }
-                    jx_ = L.f(jb * kBodyStride + kPX); jy_ = L.f(jb * kBodyStride + kPY);
-                    if (pass == 0) cand = (1u << jb) - 1u;
-                    else cand = (jx_ < 2.5 ? 0x1C3u : 0u) | (jx_ > kWidth - 2.5 ? 0xE18u : 0u) | (jy_ < 2.5 ? 0x020u : 0u) | (jy_ > kHeight - 2.5 ? 0x004u : 0u);
-                    continue;
-                }
+        for (int jb = 0; jb < B; ++jb) {
+            const double jx = L.f(jb * kBodyStride + kPX), jy = L.f(jb * kBodyStride + kPY);
+            // segments 0 / 3 (x = 0 / 105, y in [0, 24]) need y < 26.5; 1 / 4 (y in [44, 68]) need y > 41.5; the goal boxes
+            // {6, 7, 8} / {9, 10, 11} (y in [24, 44], x beyond the line) need 21.5 < y < 46.5
+            const uint32_t ylo = jy < 26.5 ? 0x009u : 0u, yhi = jy > 41.5 ? 0x012u : 0u, ymid = (jy > 21.5 && jy < 46.5) ? 0xFC0u : 0u;
+            uint32_t cand = ((jx < 2.5 ? 0x1C3u : 0u) | (jx > kWidth - 2.5 ? 0xE18u : 0u)) & (ylo | yhi | ymid);
+            cand |= (jy < 2.5 ? 0x020u : 0u) | (jy > kHeight - 2.5 ? 0x004u : 0u);
+            const double mind = (jb == ball ? kRBall : kRPlayer) + kRSeg;
+            while (cand != 0u) {
                 const int ii = __ffs((int)cand) - 1;
                 cand &= cand - 1u;
-                double tx, ty, pax, pay, mind;
-                if (pass == 0) {
-                    pax = L.f(ii * kBodyStride + kPX); pay = L.f(ii * kBodyStride + kPY); tx = jx_; ty = jy_;
-                    mind = kRPlayer + (jb == ball ? kRBall : kRPlayer);   // a = ii < jb: only b can be the ball
-                } else {
-                    pax = jx_; pay = jy_; seg_closest(ii, pax, pay, tx, ty);
-                    mind = (jb == ball ? kRBall : kRPlayer) + kRSeg;
-                }
-                const double dx = dsub(tx, pax), dy = dsub(ty, pay);
-                const double distsq = dadd(dmul(dx, dx), dmul(dy, dy));
-                if (!(distsq < mind * mind)) continue;
-                hits |= (uint64_t)((uint32_t)pass | ((uint32_t)jb << 1) | ((uint32_t)ii << 6)) << (16 * nh);
-                nh += 1;
+                double tx, ty;
+                seg_closest(ii, jx, jy, tx, ty);
+                const double dx = dsub(tx, jx), dy = dsub(ty, jy);
+                if (dadd(dmul(dx, dx), dmul(dy, dy)) < mind * mind) record(1u | ((uint32_t)jb << 1) | ((uint32_t)ii << 6));
             }
+        }
+    }
+    // 5. arbiter pre-step for the recorded pairs (uses the velocities before step 6)
+    {
+        // one copy of the block for every contact: the code of contact h comes from, and the finished contact goes to,
+        // c0 / c1 / c2 (h < REGC) or the local-memory list
 #pragma unroll 1
-            for (int h = 0; h < nh; ++h) {
-                const uint32_t code = (uint32_t)(hits >> (16 * h)) & 0xffffu;
-                const int hp = (int)(code & 1u), hj = (int)((code >> 1) & 31u), ii = (int)(code >> 6);
-                if (nc == kMaxContacts) { overflow += 1; continue; }
-                int a, b, q;                                             // b < 0: static segment -1 - b
-                if (hp == 0) { a = ii; b = hj; q = hj * (hj - 1) / 2 + ii; }
-                else { a = hj; b = -1 - ii; q = CC + hj * kNSeg + ii; }
-                // cached arbiter of the pair, requested first: the ~90 instructions below run under the HBM latency
-                // (at the end of the block the two loads were 12 % of the 5v5 kernel's stall samples)
-                const uint32_t last = C.last[(size_t)q * C.stride];
-                const double cached = C.jn[(size_t)q * C.stride];
-                const int ao = a * kBodyStride;
-                const double pax = L.f(ao + kPX), pay = L.f(ao + kPY);
-                const double ra = a == ball ? kRBall : kRPlayer;
-                double rb, tx, ty;                                       // (tx, ty): centre of b or closest point
-                if (b >= 0) { rb = b == ball ? kRBall : kRPlayer; tx = L.f(b * kBodyStride + kPX); ty = L.f(b * kBodyStride + kPY); }
-                else { rb = kRSeg; seg_closest(ii, pax, pay, tx, ty); }
-                const double dx = dsub(tx, pax), dy = dsub(ty, pay);
-                const double distsq = dadd(dmul(dx, dx), dmul(dy, dy));
-                Contact k;
-                const double dist = sqrt0(distsq);
-                if (dist != 0.0) { const double inv = fdiv(1.0, dist); k.nx = dmul(dx, inv); k.ny = dmul(dy, inv); }
-                else if (b >= 0) { k.nx = 1.0; k.ny = 0.0; }
-                else {   // segment normal: perp(normalize(b - a))
-                    double sax, say, sbx, sby;
-                    segment(ii, sax, say, sbx, sby);
-                    const double sx = dsub(sbx, sax), sy = dsub(sby, say), sl = dsqrt(dadd(dmul(sx, sx), dmul(sy, sy)));
-                    k.nx = -ddiv(sy, sl); k.ny = ddiv(sx, sl);
-                }
-                k.a = a; k.b = b;
-                const double p1x = dadd(pax, dmul(k.nx, ra)), p1y = dadd(pay, dmul(k.ny, ra));
-                const double p2x = dadd(tx, dmul(k.nx, -rb)), p2y = dadd(ty, dmul(k.ny, -rb));
-                const double pen = dadd(dmul(dsub(p2x, p1x), k.nx), dmul(dsub(p2y, p1y), k.ny));
-                // 1 / (m_inv_a + m_inv_b): four possible pairs of masses, each quotient folded by the compiler (IEEE)
-                const double nm_pp = 1.0 / (m_inv_p + m_inv_p), nm_pb = 1.0 / (m_inv_p + m_inv_b), nm_ps = 1.0 / (m_inv_p + 0.0),
-                    nm_bs = 1.0 / (m_inv_b + 0.0);
-                k.n_mass = b >= 0 ? ((a == ball || b == ball) ? nm_pb : nm_pp) : (a == ball ? nm_bs : nm_ps);
-                double m = dadd(pen, kSlop);
-                m = m < 0.0 ? m : 0.0;                                   // cpfmin(0, dist + slop)
-                const double bnum = dmul(-P.bias_coef, m);               // -0.0 unless the pair overlaps by more than the slop
-                const bool bz = bnum == 0.0;
-                const double bq = fdiv(pick(bz, 1.0, bnum), kDt);
-                k.bias = bz ? bnum : bq;                                 // 0 / dt = that same zero, kept off the divider's slow path
-                k.jbias = 0.0;
-                const double vbx = b >= 0 ? L.f(b * kBodyStride + kVX) : 0.0, vby = b >= 0 ? L.f(b * kBodyStride + kVY) : 0.0;
-                const double el = b >= 0 ? kElasticity * kElasticity : kElasticity * 0.0;
-                k.bounce = dmul(dadd(dmul(dsub(vbx, L.f(ao + kVX)), k.nx), dmul(dsub(vby, L.f(ao + kVY)), k.ny)), el);
-                // cached arbiter (collision_persistence = 3): a pair that touched within 3 steps inherits its impulse;
-                // it is warm-started with it only if it touched in the previous step too
-                k.jn = (s.stamp - last <= 3u) ? cached : 0.0;
-                k.q = q | (s.stamp - last == 1u ? kWarmBit : 0);
-                C.last[(size_t)q * C.stride] = s.stamp;
-                if (REGC > 0 && nc == 0) c0 = k; else if (REGC > 1 && nc == 1) c1 = k; else if (REGC > 2 && nc == 2) c2 = k;
-                else con[nc - REGC] = k;
-                nc += 1;
+        for (int h = 0; h < nc; ++h) {
+            Contact k;
+            const uint32_t code = (uint32_t)((REGC > 0 && h == 0) ? c0.q : ((REGC > 1 && h == 1) ? c1.q : ((REGC > 2 && h == 2) ? c2.q : con[h - REGC].q)));
+            const int hp = (int)(code & 1u), hj = (int)((code >> 1) & 31u), ii = (int)(code >> 6);
+            int a, b, q;                                                 // b < 0: static segment -1 - b
+            if (hp == 0) { a = ii; b = hj; q = hj * (hj - 1) / 2 + ii; }
+            else { a = hj; b = -1 - ii; q = CC + hj * kNSeg + ii; }
+            // cached arbiter of the pair, requested first: the ~90 instructions below run under the HBM latency
+            const CacheRec cached = cache_load(C, q);
+            const int ao = a * kBodyStride;
+            const double pax = L.f(ao + kPX), pay = L.f(ao + kPY);
+            const double ra = a == ball ? kRBall : kRPlayer;
+            double rb, tx, ty;                                           // (tx, ty): centre of b or closest point
+            if (b >= 0) { rb = b == ball ? kRBall : kRPlayer; tx = L.f(b * kBodyStride + kPX); ty = L.f(b * kBodyStride + kPY); }
+            else { rb = kRSeg; seg_closest(ii, pax, pay, tx, ty); }
+            const double dx = dsub(tx, pax), dy = dsub(ty, pay);
+            const double distsq = dadd(dmul(dx, dx), dmul(dy, dy));
+            const double dist = sqrt0(distsq);
+            if (dist != 0.0) { const double inv = fdiv(1.0, dist); k.nx = dmul(dx, inv); k.ny = dmul(dy, inv); }
+            else if (b >= 0) { k.nx = 1.0; k.ny = 0.0; }
+            else {   // segment normal: perp(normalize(b - a))
+                double sax, say, sbx, sby;
+                segment(ii, sax, say, sbx, sby);
+                const double sx = dsub(sbx, sax), sy = dsub(sby, say), sl = dsqrt(dadd(dmul(sx, sx), dmul(sy, sy)));
+                k.nx = -ddiv(sy, sl); k.ny = ddiv(sx, sl);
             }
+            k.a = a; k.b = b;
+            const double p1x = dadd(pax, dmul(k.nx, ra)), p1y = dadd(pay, dmul(k.ny, ra));
+            const double p2x = dadd(tx, dmul(k.nx, -rb)), p2y = dadd(ty, dmul(k.ny, -rb));
+            const double pen = dadd(dmul(dsub(p2x, p1x), k.nx), dmul(dsub(p2y, p1y), k.ny));
+            // 1 / (m_inv_a + m_inv_b): four possible pairs of masses, each quotient folded by the compiler (IEEE)
+            const double nm_pp = 1.0 / (m_inv_p + m_inv_p), nm_pb = 1.0 / (m_inv_p + m_inv_b), nm_ps = 1.0 / (m_inv_p + 0.0),
+                nm_bs = 1.0 / (m_inv_b + 0.0);
+            k.n_mass = b >= 0 ? ((a == ball || b == ball) ? nm_pb : nm_pp) : (a == ball ? nm_bs : nm_ps);
+            double m = dadd(pen, kSlop);
+            m = m < 0.0 ? m : 0.0;                                       // cpfmin(0, dist + slop)
+            const double bnum = dmul(-P.bias_coef, m);                   // -0.0 unless the pair overlaps by more than the slop
+            const bool bz = bnum == 0.0;
+            const double bq = fdiv(pick(bz, 1.0, bnum), kDt);
+            k.bias = bz ? bnum : bq;                                     // 0 / dt = that same zero, kept off the divider's slow path
+            k.jbias = 0.0;
+            const double vbx = b >= 0 ? L.f(b * kBodyStride + kVX) : 0.0, vby = b >= 0 ? L.f(b * kBodyStride + kVY) : 0.0;
+            const double el = b >= 0 ? kElasticity * kElasticity : kElasticity * 0.0;
+            k.bounce = dmul(dadd(dmul(dsub(vbx, L.f(ao + kVX)), k.nx), dmul(dsub(vby, L.f(ao + kVY)), k.ny)), el);
+            // cached arbiter (collision_persistence = 3): a pair that touched within 3 steps inherits its impulse;
+            // it is warm-started with it only if it touched in the previous step too
+            k.jn = (s.stamp - cached.last <= 3u) ? cached.jn : 0.0;
+            k.q = q | (s.stamp - cached.last == 1u ? kWarmBit : 0);
+            if (REGC > 0 && h == 0) c0 = k; else if (REGC > 1 && h == 1) c1 = k; else if (REGC > 2 && h == 2) c2 = k;
+            else con[h - REGC] = k;
         }
     }
     // 6. integrate velocities through velocity_func (player.py:45-50, ball.py:49-54)
@@ -508,8 +543,11 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
         const int o = i * kBodyStride;
         double vx = dadd(dmul(L.f(o + kVX), P.damping_dt), 0.0), vy = dadd(dmul(L.f(o + kVY), P.damping_dt), 0.0);
         const double l2 = dadd(dmul(vx, vx), dmul(vy, vy));
-        const double l = sqrt0(l2), mx = i == ball ? kBallMaxV : kPlayerMaxV;
-        if (l > mx) { const double sc = fdiv(mx, l); vx = dmul(vx, sc); vy = dmul(vy, sc); }
+        // `sqrt(l2) > max` decided on l2 (IEEE sqrt is monotone: the bound is exact); the root is taken only to clamp
+        if (l2 > (i == ball ? P.clamp_sq_ball : P.clamp_sq_player)) {
+            const double mx = i == ball ? kBallMaxV : kPlayerMaxV, sc = fdiv(mx, fsqrt(l2));
+            vx = dmul(vx, sc); vy = dmul(vy, sc);
+        }
         L.f(o + kVX) = vx; L.f(o + kVY) = vy;
     }
     // 7. warm start (cpArbiterApplyCachedImpulse, dt_coef = 1)
@@ -528,11 +566,11 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
 #pragma unroll 1
             for (int i = REGC; i < nc; ++i) solve_contact(L, con[i - REGC], ball);
         }
-        if (REGC > 0) C.jn[(size_t)(c0.q & kPairMask) * C.stride] = c0.jn;
-        if (REGC > 1 && nc > 1) C.jn[(size_t)(c1.q & kPairMask) * C.stride] = c1.jn;
-        if (REGC > 2 && nc > 2) C.jn[(size_t)(c2.q & kPairMask) * C.stride] = c2.jn;
+        if (REGC > 0) cache_store(C, c0.q & kPairMask, c0.jn, s.stamp);
+        if (REGC > 1 && nc > 1) cache_store(C, c1.q & kPairMask, c1.jn, s.stamp);
+        if (REGC > 2 && nc > 2) cache_store(C, c2.q & kPairMask, c2.jn, s.stamp);
 #pragma unroll 1
-        for (int i = REGC; i < nc; ++i) C.jn[(size_t)(con[i - REGC].q & kPairMask) * C.stride] = con[i - REGC].jn;
+        for (int i = REGC; i < nc; ++i) cache_store(C, con[i - REGC].q & kPairMask, con[i - REGC].jn, s.stamp);
     }
     s.stamp += 1;
     return nc;
@@ -554,7 +592,7 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
     double init_d[kMaxN];                                                // :433
     const double bix = L.f(bo + kPX), biy = L.f(bo + kPY);               // :435
 #pragma unroll 1
-    for (int i = 0; i < N; ++i) {
+    for (int i = (N == 5 ? 3 : 0); i < N; ++i) {                         // only the players get_team_reward looks at (:501-504)
         const double dx = dsub(L.f(i * kBodyStride + kPX), bix), dy = dsub(L.f(i * kBodyStride + kPY), biy);
         init_d[i] = sqrt0(dadd(dmul(dx, dx), dmul(dy, dy)));
     }
@@ -569,6 +607,8 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
         for (int p = 0; p < kMaxN; ++p)
             if (p < N) { const uint32_t w = pair[p]; packed |= (uint64_t)(((w & 0xffu) % 5u) | ((((w >> 8) & 0xffu) % 5u) << 3)) << (6 * p); }
     }
+    Philox4 blk;                                                         // one Philox block = the actions of two players
+    blk.x = blk.y = blk.z = blk.w = 0u;
 #pragma unroll 1
     for (int p = 0; p < 2 * N; ++p) {                                    // :447-453, right team = action_space.sample() (:429)
         int arrow, key;
@@ -577,7 +617,7 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
         else {
             const uint32_t stream = p < N ? kStreamActions : kStreamV1Opp;
             const int q = p < N ? p : p - N;
-            const Philox4 blk = philox_step_block(P.key, env_id, stream, s.t_total, (uint32_t)(2 * q) >> 2);
+            if ((q & 1) == 0) blk = philox_step_block(P.key, env_id, stream, s.t_total, (uint32_t)q >> 1);
             const uint32_t w0 = (q & 1) ? blk.z : blk.x, w1 = (q & 1) ? blk.w : blk.y;
             arrow = (int)__umulhi(w0, 5u); key = (int)__umulhi(w1, 5u);
         }
@@ -585,8 +625,17 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
     }
 
     bool out = false;                                                    // check_and_fix_out_bounds, :256-287
+    // only boundary segments the ball can reach (r + r_segment = 2) are tested, in the reference's order (first hit wins)
+    uint32_t ocand;
+    {
+        const double bx = L.f(bo + kPX), by = L.f(bo + kPY);
+        ocand = ((bx < 2.0 ? 0x03u : 0u) | (bx > kWidth - 2.0 ? 0x18u : 0u)) & ((by < 26.0 ? 0x09u : 0u) | (by > 42.0 ? 0x12u : 0u));
+        ocand |= (by > kHeight - 2.0 ? 0x04u : 0u) | (by < 2.0 ? 0x20u : 0u);
+    }
 #pragma unroll 1
-    for (int sg = 0; sg < 6 && !out; ++sg) {
+    while (ocand != 0u && !out) {
+        const int sg = __ffs((int)ocand) - 1;
+        ocand &= ocand - 1u;
         if (!ball_touches_segment(L, ball, sg)) continue;
         out = true;
         const double bx = L.f(bo + kPX), by = L.f(bo + kPY);
@@ -619,8 +668,16 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
     }
 
     bool goal = false;                                                   // ball_contact_goal, :291-296
+    {   // the goal-box segments lie beyond the goal lines between y = 24 and y = 44: reachable only from x < 2 or x > 103
+        const double bx = L.f(bo + kPX), by = L.f(bo + kPY);
+        uint32_t gcand = ((bx < 2.0 ? 0x1C0u : 0u) | (bx > kWidth - 2.0 ? 0xE00u : 0u)) & ((by > 22.0 && by < 46.0) ? 0xFC0u : 0u);
 #pragma unroll 1
-    for (int sg = 6; sg < 12; ++sg) goal = goal || ball_touches_segment(L, ball, sg);
+        while (gcand != 0u && !goal) {
+            const int sg = __ffs((int)gcand) - 1;
+            gcand &= gcand - 1u;
+            goal = ball_touches_segment(L, ball, sg);
+        }
+    }
     if (goal) {                                                          // :469-475
         const bool left_scored = L.f(bo + kPX) > kWidth - 2;
         reward = dadd(reward, left_scored ? 1000.0 : -1000.0);

@@ -239,9 +239,27 @@ class FutbolV1VecEnv(FutbolVecEnv):
             _lib.check(self.lib.futbol_create(C.byref(self.cfg), C.byref(h)))
         self._h = h
         self.obs_dim, self.act_shape = 4 + 8 * self.number_of_player, (2 * self.number_of_player,)
+        self.STATE_DTYPE = _lib.v1_env_state_dtype(self.number_of_player)
+        assert self.STATE_DTYPE.itemsize == self.lib.futbol_env_state_bytes(h)
         self._alloc()
         self.observation_space = spaces.Box(low=-1.0, high=1.0, shape=(self.obs_dim,), dtype=np.float32)
         self.action_space = spaces.MultiDiscrete([5, 5] * self.number_of_player)
 
     def set_state(self, records):
-        raise _lib.FutbolError("set_state is not available for the v1 variant (the arbiter cache is not exported)")
+        """Restores every env from records of ``get_state()`` (bodies, counters and the arbiter cache); synchronises."""
+        records = np.ascontiguousarray(records, dtype=self.STATE_DTYPE)
+        if records.shape != (self.num_envs,):
+            raise ValueError("need %d state records" % self.num_envs)
+        B = 2 * self.number_of_player + 1
+        for vals in (records["body"][:, :B], records["jn"]):       # same domain rule as v0 (guard-free division / square root)
+            mag = np.abs(vals)
+            if not np.isfinite(vals).all() or (mag > 1e6).any() or ((mag != 0) & (mag < 1e-60)).any():
+                raise ValueError("state values must be finite, at most 1e6 in magnitude and either zero or at least 1e-60")
+        if (records["owner_side"] > 1).any() or (records["ep_step"] < 0).any():
+            raise ValueError("owner_side must be 0 / 1 and ep_step non-negative")
+        if (records["stamp"] < 8).any() or (records["last"] > records["stamp"][:, None]).any():
+            raise ValueError("stamp counts from 8 and no pair can have touched after it")
+        aos = torch.from_numpy(records.view(np.uint8).copy()).to(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.futbol_set_state(self._h, _ptr(self.state), _ptr(aos), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()

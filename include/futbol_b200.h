@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FUTBOL_ABI_VERSION 1
+#define FUTBOL_ABI_VERSION 2
 
 enum { FUTBOL_VARIANT_V0 = 0, /* FutbolEnv: 2v2 kinematic, possession state machine */
        FUTBOL_VARIANT_V1 = 1  /* Futbol: NvN, circle/segment rigid-body physics     */ };
@@ -68,16 +68,21 @@ typedef struct FutbolV0EnvState {
     uint8_t  pad_;
 } FutbolV0EnvState;
 
-/* One env's v1 state (bodies + scalars; the arbiter cache is not exported), for futbol_get_state.
- * Bodies: team A players 0..N-1, team B players N..2N-1, ball 2N; unused rows are zero. */
+/* One env's v1 state, for futbol_get_state / futbol_set_state: this header, followed by the arbiter cache of the
+ * env's P = B(B-1)/2 + 12 B shape pairs (B = 2N + 1 bodies):  double jn[P]; uint32_t last[P];  then padding to a
+ * multiple of 8 bytes.  futbol_env_state_bytes() is the size of one whole record.
+ * Bodies: team A players 0..N-1, team B players N..2N-1, ball 2N; unused rows are zero.
+ * Pair ids: circle/circle (i < j) -> j(j-1)/2 + i; circle/segment -> B(B-1)/2 + 12 body + segment (segments in the
+ * order of _setup_walls, envs_v1/futbol_env.py:184-224).  jn = the normal impulse the pair accumulated the last
+ * time it touched; last = the stamp of that space step (0 = never). */
 typedef struct FutbolV1EnvState {
     double   body[21][6];  /* x, y, vx, vy, v_bias_x, v_bias_y */
     uint64_t t_total;      /* steps since creation = Philox step index */
-    uint32_t stamp;        /* space steps taken (0.1 s steps and the 1e-4 s kick-off steps) */
+    uint32_t stamp;        /* space steps taken (0.1 s steps and the 1e-4 s kick-off steps), counted from 8 */
     int32_t  ep_step;
     uint8_t  owner_side;   /* ball_owner_side: 0 left, 1 right (envs_v1/futbol_env.py:147) */
     uint8_t  flags;        /* of the last step: 1 goal, 2 out of bounds, 4 done, 8 the goal was scored by the left team */
-    uint8_t  pad_[2];
+    uint8_t  pad_[6];
 } FutbolV1EnvState;
 
 /* Rollout statistics (sums over all envs and steps of one futbol_rollout call).
@@ -138,9 +143,9 @@ int futbol_rollout_vs(FutbolHandle *h, void *state, int K, const uint8_t *action
 /* ---- state access (device AoS records: FutbolV0EnvState / FutbolV1EnvState) ---------- */
 size_t futbol_env_state_bytes(const FutbolHandle *h); /* sizeof one AoS record */
 int futbol_get_state(FutbolHandle *h, const void *state, void *aos_out, void *stream);
-/* v0 only.  Values must be pitch-scale: finite, |value| <= 1e6 and either zero or >= 1e-60 (the kernel's
- * correctly rounded division / square root run without a range guard, csrc/ieee_fast.cuh); the Python
- * binding validates this on the host before the call. */
+/* Values must be pitch-scale: finite, |value| <= 1e6 and either zero or >= 1e-60 (the kernel's correctly rounded
+ * division / square root run without a range guard, csrc/ieee_fast.cuh); the Python binding validates this on the
+ * host before the call. */
 int futbol_set_state(FutbolHandle *h, void *state, const void *aos_in, void *stream);
 
 /* ---- rollout-buffer glue: generalised advantage estimation -----------------------------

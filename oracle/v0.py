@@ -39,7 +39,15 @@ def build(force=False):
     if force or not os.path.exists(_LIB_PATH) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
             for f in ("futbol_v0_oracle.c", "futbol_v1_oracle.c", "Makefile")):
-        subprocess.run(["make", "-C", _HERE, "-B", "CC=gcc"], check=True, capture_output=True)
+        import fcntl
+        with open(_LIB_PATH + ".lock", "w") as lock:          # several processes may get here at once (torchrun, xdist)
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                tmp = "libfutbol_oracle.so.tmp.%d" % os.getpid()
+                subprocess.run(["make", "-C", _HERE, "-B", "CC=gcc", "TARGET=" + tmp, tmp], check=True, capture_output=True)
+                os.replace(os.path.join(_HERE, tmp), _LIB_PATH)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return _LIB_PATH
 
 

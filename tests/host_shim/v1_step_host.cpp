@@ -8,6 +8,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __align__(n) __attribute__((aligned(n)))
 #define __noinline__
 #define FUTBOL_LANES 1
 #define FUTBOL_HOST_SHIM 1
@@ -35,23 +36,29 @@ void host_v1_rollout(uint64_t seed, uint32_t env_id0, int n_players, int ep_limi
     std::memset(&P, 0, sizeof(P));
     P.seed = seed; P.key = philox_expand_key(seed); P.env_id_offset = env_id0; P.n_envs = n; P.n_players = n_players;
     P.ep_limit = ep_limit; P.auto_reset = 1; P.damping_dt = damping_dt; P.bias_coef = bias_coef;
+    for (int which = 0; which < 2; ++which) {      // largest s with sqrt(s) <= max (capi.cu computes the same bound)
+        const double mx = which ? kBallMaxV : kPlayerMaxV;
+        double sq = mx * mx;
+        while (std::sqrt(sq) > mx) sq = std::nextafter(sq, -INFINITY);
+        while (std::sqrt(std::nextafter(sq, INFINITY)) <= mx) sq = std::nextafter(sq, INFINITY);
+        (which ? P.clamp_sq_ball : P.clamp_sq_player) = sq;
+    }
     for (int i = 0; i < 2 * n_players; ++i) { P.form_x[i] = form_x[i]; P.form_y[i] = form_y[i]; }
     const int N = n_players, B = 2 * N + 1, D = 4 + 8 * N, NP = n_pairs(B);
     const Lane L = make_lane(0, 0, N);
     const uint32_t form_base = stage_formation(P, 1, 0, 1);
-    std::vector<double> jn(NP);
-    std::vector<uint32_t> last(NP);
+    std::vector<CacheRec> cache(NP);
     Contact con[kMaxContacts];
     for (int i = 0; i < n; ++i) {
-        std::fill(jn.begin(), jn.end(), 0.0);
-        std::fill(last.begin(), last.end(), 0u);
-        PairCache C{jn.data(), last.data(), 1};
+        std::memset(cache.data(), 0, NP * sizeof(CacheRec));
+        PairCache C{cache.data(), 1};
         V1Regs s;
         const uint32_t env_id = env_id0 + (uint32_t)i;
         init_env(L, s, P, env_id, form_base);
         for (int k = 0; k < steps; ++k) {
             const size_t slot = (size_t)k * n + i;
-            const StepResult r = (N >= 4) ? v1_step<2>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con, form_base)
+            const StepResult r = (N >= 7) ? v1_step<3>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con, form_base)
+                                 : (N >= 4) ? v1_step<2>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con, form_base)
                                  : (N >= 2) ? v1_step<1>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con, form_base)
                                           : v1_step<0>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con, form_base);
             if (r.done) reset_env(L, s, P, env_id, form_base);

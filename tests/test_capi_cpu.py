@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(L, name), name
     assert set(names) == set(_lib.EXPORTS)
-    assert L.futbol_abi_version() == 1
+    assert L.futbol_abi_version() == 2
 
 
 def test_struct_mirrors_match_header_sizes():
@@ -35,6 +35,9 @@ def test_struct_mirrors_match_header_sizes():
     assert _lib.STATS_DTYPE.itemsize == C.sizeof(_lib.FutbolStats) == 64
     assert _lib.V0_ENV_STATE.fields["t_total"][1] == 200 and _lib.V0_ENV_STATE.fields["owner"][1] == 220
     assert _lib.V1_ENV_STATE.itemsize == 21 * 6 * 8 + 24 and _lib.V1_ENV_STATE.fields["owner_side"][1] == 21 * 6 * 8 + 16
+    for N, P in ((1, 3 + 36), (2, 10 + 60), (5, 55 + 132), (10, 210 + 252)):      # header + jn[P] + last[P], padded to 8 bytes
+        dt = _lib.v1_env_state_dtype(N)
+        assert dt.itemsize == (1032 + 12 * P + 7) // 8 * 8 and dt.fields["jn"][1] == 1032 and dt.fields["last"][1] == 1032 + 8 * P
 
 
 def test_null_arguments_return_error_codes_without_a_gpu():

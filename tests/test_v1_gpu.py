@@ -162,6 +162,49 @@ def test_v1_and_v0_step_api_float32_outputs_ragged_batch(torch_cuda):
         assert np.array_equal(rew.cpu().numpy(), want0["reward"][t].astype(np.float32)) and np.array_equal(done.cpu().numpy(), want0["done"][t])
 
 
+@pytest.mark.parametrize("N", [1, 2, 5, 10])
+def test_v1_set_state_from_oracle_and_continue(torch_cuda, N):
+    """Checkpoint / restore incl. the arbiter cache: the oracle's mid-trajectory state (bodies, bias velocities, cached
+    impulses and their ages) is written with set_state and both continue identically; get_state -> set_state on a second
+    env gives the same continuation; out-of-domain records are refused."""
+    from gym_futbol_b200 import FutbolV1VecEnv
+    from oracle.v1 import OracleV1
+    n, seed, off, B = 96, 17, 4000, 2 * N + 1
+    P = B * (B - 1) // 2 + 12 * B
+    orc = OracleV1(n, seed=seed, env_id0=off, number_of_player=N)
+    acts = np.random.default_rng(3).integers(0, 5, (360, n, 2 * N), dtype=np.uint8)
+    orc.rollout(250, actions=acts[:250], autoreset=2, n_threads=4, record=False)
+    env = FutbolV1VecEnv(n, number_of_player=N, seed=seed, env_id_offset=off, dtype=torch_cuda.float64)
+    rec = np.zeros(n, dtype=env.STATE_DTYPE)
+    e = orc.envs
+    rec["body"][:, :B, 0:2], rec["body"][:, :B, 2:4], rec["body"][:, :B, 4:6] = e["p"][:, :B], e["v"][:, :B], e["vb"][:, :B]
+    rec["t_total"], rec["ep_step"], rec["owner_side"] = e["t_total"], e["ep_step"], e["owner_side"]
+    stamp = 1000
+    rec["stamp"] = stamp
+    age = e["age"][:, :P].astype(np.int64)
+    rec["last"] = np.where(age == 255, 0, np.maximum(stamp - 1 - age, 0))        # kernel: stamp - last = age + 1
+    rec["jn"] = e["jn"][:, :P]
+    assert (age == 0).sum() > 0 and ((age == 1) | (age == 2)).sum() > 0          # live and cached arbiters are present
+    env.set_state(rec)
+    back = env.get_state()
+    assert back.tobytes() == rec.tobytes()
+    env2 = FutbolV1VecEnv(n, number_of_player=N, seed=seed, env_id_offset=off, dtype=torch_cuda.float64)
+    env2.set_state(back)
+    want = orc.rollout(110, actions=acts[250:], autoreset=2, n_threads=4)
+    for t in range(110):
+        a = torch_cuda.from_numpy(acts[250 + t]).cuda()
+        obs, rew, done, _ = env.step(a)
+        assert np.array_equal(obs.cpu().numpy(), want["obs"][t]) and np.array_equal(rew.cpu().numpy(), want["reward"][t]), t
+        assert np.array_equal(done.cpu().numpy(), want["done"][t])
+        obs2, rew2, _, _ = env2.step(a)
+        assert torch_cuda.equal(obs, obs2) and torch_cuda.equal(rew, rew2)
+    for field, idx, val in (("body", (3, 0, 1), np.nan), ("jn", (5, 2), 1e-200), ("owner_side", (1,), 2), ("last", (0, 0), stamp + 1)):
+        bad = rec.copy()
+        bad[field][idx] = val
+        with pytest.raises(ValueError):
+            env.set_state(bad)
+
+
 # ---- against the reference's own Python (tests/golden/v1_golden.npz, see tests/test_oracle_v1_golden.py) ----------------
 def _golden_v1_cases():
     import json

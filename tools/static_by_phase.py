@@ -71,7 +71,7 @@ def main():
     tabs = chains(sub)
     fn = max(tabs, key=lambda k: len(tabs[k]))
     tab = tabs[fn]
-    execd = {}
+    execd, samples = {}, {}
     if rep:
         out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(out)))
@@ -81,7 +81,8 @@ def main():
         assert abs(len(data) - len(tab)) < 16, "report does not match the library (%d vs %d instructions)" % (len(data), len(tab))
         for r in data:
             execd[int(r[ix["Address"]], 16) - base] = int(r[ix["Instructions Executed"]])
-    per = collections.defaultdict(lambda: [0, 0, 0])      # key -> [static, static executed, dynamic]
+            samples[int(r[ix["Address"]], 16) - base] = int(r[ix["# Samples"]])
+    per = collections.defaultdict(lambda: [0, 0, 0, 0])      # key -> [static, static executed, dynamic, stall samples]
     for off, (chain, _) in tab.items():
         key = None
         for i, (f, l) in enumerate(chain):
@@ -98,13 +99,15 @@ def main():
         e = execd.get(off, 0)
         p[1] += 1 if e > 0 else 0
         p[2] += e
+        p[3] += samples.get(off, 0)
     tot = sum(p[0] for p in per.values())
     dyn = sum(p[2] for p in per.values()) or 1
+    smp = sum(p[3] for p in per.values()) or 1
     print("kernel %s: %d SASS instructions (%.1f KB)%s" % (fn[:50], tot, tot / 64.0, ", executed %d (%.1f KB)" % (
         sum(p[1] for p in per.values()), sum(p[1] for p in per.values()) / 64.0) if rep else ""))
-    print("%-22s %-22s %6s %6s %7s" % ("line in " + anchor, "callee", "static", "exec'd", "dyn%"))
-    for key, p in sorted(per.items(), key=lambda kv: -kv[1][0])[:60]:
-        print("%-22s %-22s %6d %6d %6.2f%%" % (key[0], key[1], p[0], p[1], 100.0 * p[2] / dyn))
+    print("%-22s %-22s %6s %6s %7s %7s" % ("line in " + anchor, "callee", "static", "exec'd", "dyn%", "samp%"))
+    for key, p in sorted(per.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("PHASE_TOP", 60))]:
+        print("%-22s %-22s %6d %6d %6.2f%% %6.2f%%" % (key[0], key[1], p[0], p[1], 100.0 * p[2] / dyn, 100.0 * p[3] / smp))
 
 
 if __name__ == "__main__":
