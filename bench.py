@@ -238,6 +238,8 @@ def main():
     ap.add_argument("--envs", type=int, default=TOTAL_ENVS, help="total envs of the job (default 2^20)")
     ap.add_argument("--random-opp", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the non-headline configurations (configs object)")
+    ap.add_argument("--bind-cpus", type=int, default=1, help="pin each rank to its GPU's local CPUs before allocating pinned memory")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":
@@ -299,93 +301,74 @@ def main():
     value = args.envs * K * args.steps / (elapsed_ms * 1e-3)
 
     # ---- end to end through the public API with HOST buffers (`e2e`) ----
-    # What a host-side consumer of the reference API gets: actions come from pinned host memory, and every
-    # observation, reward and done flag of the step is delivered back into pinned host memory.  The K = 64
-    # rollout is issued as E2E_CHUNKS launches of K / E2E_CHUNKS steps so that the device->host copy of one
-    # chunk (copy stream) overlaps the simulation of the next (compute stream); two device buffers alternate.
-    chunks = E2E_CHUNKS
-    Kc = K // chunks
-    h_acts = torch.randint(0, 16, (K, n_local), dtype=torch.uint8).pin_memory()
-    h_obs = torch.empty((K, n_local, 30), dtype=torch.float32).pin_memory()
-    h_rew = torch.empty((K, n_local), dtype=torch.float32).pin_memory()
-    h_done = torch.empty((K, n_local), dtype=torch.uint8).pin_memory()
-    h_stats = torch.empty(64, dtype=torch.uint8).pin_memory()
-    d_bufs = [(torch.empty((Kc, n_local), dtype=torch.uint8, device=dev),
-               torch.empty((Kc, n_local, 30), dtype=torch.float32, device=dev),
-               torch.empty((Kc, n_local), dtype=torch.float32, device=dev),
-               torch.empty((Kc, n_local), dtype=torch.uint8, device=dev)) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(dev)
-    ev_done = [torch.cuda.Event() for _ in range(2)]      # chunk simulated (compute stream)
-    ev_free = [torch.cuda.Event() for _ in range(2)]      # chunk copied out (copy stream)
-
-    def e2e_step():
-        for c in range(chunks):
-            b = c & 1
-            da, do, dr, dd = d_bufs[b]
-            ks = slice(c * Kc, (c + 1) * Kc)
-            stream.wait_event(ev_free[b])
-            da.copy_(h_acts[ks], non_blocking=True)
-            env.rollout(Kc, actions=da, out=(do, dr, dd))
-            ev_done[b].record(stream)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ev_done[b])
-                h_obs[ks].copy_(do, non_blocking=True)
-                h_rew[ks].copy_(dr, non_blocking=True)
-                h_done[ks].copy_(dd, non_blocking=True)
-                ev_free[b].record(copy_stream)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_done[(chunks - 1) & 1])
-            h_stats.copy_(env.stats, non_blocking=True)
-        copy_stream.synchronize()                # the host consumer holds the whole step before the next begins
-
-    for b in range(2):
-        ev_free[b].record(copy_stream)
+    # What a host-side consumer of the reference API gets (gym_futbol_b200/host_io.py): actions come from pinned host
+    # memory, and every observation, reward and done flag of the step is delivered back into pinned host memory, the copy
+    # of one chunk overlapped with the simulation of the next.
+    from gym_futbol_b200 import host_io
+    local_cpus = host_io.bind_to_local_cpus(local_rank) if args.bind_cpus else None   # before the pinned allocations
+    pipe = host_io.HostRollout(env, K, chunks=E2E_CHUNKS)
+    pipe.h_actions.copy_(torch.randint(0, 16, (K, n_local), dtype=torch.uint8))
+    d2h_peak = host_io.measure_d2h_peak(dev, nbytes=1 << 30, reps=3, barrier=barrier)   # all ranks copy at once
     for _ in range(2):
-        e2e_step()
+        pipe.run()
     barrier()
     e2e_steps = max(2, min(args.steps, 5))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(e2e_steps):
-        e2e_step()
-    e1.record(copy_stream)                       # the last device->host copy of the last step ends here
+        pipe.run()                                   # the host consumer holds the whole step before the next begins
+    e1.record(pipe.copy_stream)                      # the last device->host copy of the last step ends here
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    t = torch.tensor([e0.elapsed_time(e1), -d2h_peak], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = args.envs * K * e2e_steps / (t.item() * 1e-3)
-    e2e_launches = chunks * e2e_steps
-
-    # the same loop with observations left in HBM for an on-device policy (the zero-copy use north_star describes)
-    def resident_step():
-        da = d_bufs[0][0]
-        for c in range(chunks):
-            da.copy_(h_acts[c * Kc:(c + 1) * Kc], non_blocking=True)
-            env.rollout(Kc, actions=da)
-        h_stats.copy_(env.stats, non_blocking=True)
-        stream.synchronize()
+    e2e_ms, d2h_peak_min = t[0].item(), -t[1].item()
+    e2e_value = args.envs * K * e2e_steps / (e2e_ms * 1e-3)
+    e2e_launches = E2E_CHUNKS * e2e_steps
+    d2h_rate = pipe.d2h_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9       # per GPU
 
     for _ in range(2):
-        resident_step()
+        pipe.run_resident()
     barrier()
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     r0.record(stream)
     for _ in range(e2e_steps):
-        resident_step()
+        pipe.run_resident()
     r1.record(stream)
     barrier()
     t = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     resident_value = args.envs * K * e2e_steps / (t.item() * 1e-3)
-    clocks = sampler.stop() if rank == 0 else None      # sampled across all three timed regions (value, e2e, resident)
 
     stats = torch.from_numpy(env.stats.cpu().numpy().view("int64").copy()).to(dev)   # optional statistics gather
     if world > 1:
         dist.all_reduce(stats[1:6], op=dist.ReduceOp.SUM)
+    slices = env.rollout_slices(K)
+    h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
+    del pipe, acts
+    env.close()
+    del env
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configurations, timed in the same clock-sampled run (rank 0 of a 1-GPU run) ----
+    peak, peak_src = measured_peaks()
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = {}
+        for name, fn in (("step_api_4096", lambda: bench_step_api(torch, dev, peak)),
+                         ("v1_2v2_2p20", lambda: bench_v1_rollout(torch, dev, peak, 2, 1 << 20)),
+                         ("v1_5v5_2p18", lambda: bench_v1_rollout(torch, dev, peak, 5, 1 << 18)),
+                         ("v1_10v10_2p16", lambda: bench_v1_rollout(torch, dev, peak, 10, 1 << 16)),
+                         ("ppo_65536", lambda: bench_ppo(torch, dev))):
+            try:
+                configs[name] = fn()
+            except Exception as exc:  # noqa: BLE001  (a failing side configuration must not lose the headline line)
+                configs[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            torch.cuda.empty_cache()
+    clocks = sampler.stop() if rank == 0 else None      # sampled across every timed region of this process
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
         achieved = n_local * K * BYTES_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -397,19 +380,25 @@ def main():
                        "envs_per_gpu": n_local, "rollout_k": K, "parallelism": "env-sharded x%d, no collective" % world,
                        "l2": "each step writes %.2f GB per GPU (obs/reward/done), larger than the 126 MB L2"
                              % (n_local * K * 125 / 1e9)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_acts.numel()) * world,
-                    "d2h_bytes_per_step": int(h_obs.numel() * 4 + h_rew.numel() * 4 + h_done.numel() + 64) * world,
-                    "launches_per_step": chunks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes) * world,
+                    "d2h_bytes_per_step": int(d2h_bytes) * world, "launches_per_step": E2E_CHUNKS,
                     "note": "pinned-host actions in; EVERY observation, reward and done flag of the step copied back to "
-                            "pinned host memory (PCIe-bound), copy of chunk c overlapped with simulation of chunk c+1",
+                            "pinned host memory (host-link bound), copy of chunk c overlapped with simulation of chunk c+1 "
+                            "(gym_futbol_b200.host_io.HostRollout)",
+                    "roofline": {"bound": "host link (device->host)", "achieved": d2h_rate, "peak": d2h_peak_min, "unit": "GB/s per GPU",
+                                 "frac": d2h_rate / d2h_peak_min if d2h_peak_min > 0 else None,
+                                 "peak_source": "pinned 1 GiB device->host copies timed in this process, all %d ranks copying at "
+                                                "the same time, slowest rank's best of 3" % world,
+                                 "cpu_affinity": "GPU-local CPUs %s" % (("%d-%d" % (local_cpus[0], local_cpus[-1])) if local_cpus else "not set")},
                     "obs_resident_in_hbm": {"value": resident_value, "unit": UNIT,
                                             "note": "same loop, observations consumed on the device (zero-copy policy): "
                                                     "host actions in, statistics out"}},
             "gpu_launches": int(launches), "gpu_launches_e2e": int(e2e_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(n_local, K), "peak_source": peak_src, "kernel": ("v0_rollout_sliced_kernel (the same step code; (time slice, env block) units from a work queue)"
-                                    if 740 < (n_local + 127) // 128 < 6 * 740 else "v0_rollout_kernel"),
+                         "traffic": measured_traffic(n_local, K), "peak_source": peak_src,
+                         "kernel": ("v0_rollout_sliced_kernel (the same step code; (time slice, env block) units from a work queue, "
+                                    "%d slices)" % slices) if slices > 1 else "v0_rollout_kernel",
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": n_local * K * BYTES_PER_ENV_STEP,
                          "note": "the kernel is instruction-issue bound (fp64 IEEE sqrt/div sequences, selects, Philox), "
@@ -418,11 +407,143 @@ def main():
             "rollout_stats": {"episodes": int(stats[2]), "goals_ai": int(stats[3]), "goals_opp": int(stats[4]),
                               "out_of_field": int(stats[5])},
         }
+        if configs is not None:
+            out["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_port_baseline()
+            out["cpu_baseline_reference"] = cpu_reference_baseline()
         _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------- the other configs
+def _timed(torch, fn, reps):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def bench_step_api(torch, dev, peak, n=4096, steps=1000):
+    """BASELINE.json configs[1]: v0 vs hard-coded opponents, 4096 envs, 100 warm-up + 1000 timed steps through the PER-STEP
+    API (one launch per step, state round-trips HBM: 572 B per env-step), eager and as CUDA graphs of 100 steps, and the
+    same 1000 steps as one fused rollout."""
+    from gym_futbol_b200 import FutbolVecEnv
+    env = FutbolVecEnv(n, device=dev, seed=0, random_opp=False)
+    env.reset()
+    acts = torch.randint(0, 16, (steps, n), dtype=torch.uint8, device=dev)
+    for t in range(100):
+        env.step(acts[t])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for t in range(steps):
+        env.step(acts[t])
+    b.record()
+    torch.cuda.synchronize()
+    wall_us = (time.perf_counter() - t0) / steps * 1e6
+    eager_us = a.elapsed_time(b) / steps * 1e3
+    g, side = torch.cuda.CUDAGraph(), torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for t in range(100):
+                env.step(acts[t])
+    torch.cuda.current_stream(dev).wait_stream(side)
+    g.replay()
+    graph_us = _timed(torch, g.replay, 20) / 100 * 1e3
+    env.rollout(steps, actions=acts)
+    fused_ms = _timed(torch, lambda: env.rollout(steps, actions=acts), 10)
+    bpe = 126 + 2 * STATE_BYTES_PER_ENV
+    out = {"workload": "v0 2v2 vs hard-coded opponents, %d envs, per-step API" % n, "timed_steps": steps,
+           "eager": {"us_per_step_device": eager_us, "us_per_step_wall": wall_us, "env_steps_per_s": n / (wall_us * 1e-6),
+                     "note": "one Python call + one launch per step; bound by the host call"},
+           "cuda_graph_100_steps": {"us_per_step": graph_us, "env_steps_per_s": n / (graph_us * 1e-6), "replays_timed": 20,
+                                    "hbm_frac": n / (graph_us * 1e-6) * bpe / 1e9 / peak},
+           "fused_rollout_k1000": {"ms": fused_ms, "env_steps_per_s": n * steps / (fused_ms * 1e-3), "launches_timed": 10},
+           "bytes_per_env_step": bpe, "grid": "%d blocks on the GPU's SMs" % ((n + 127) // 128)}
+    env.close()
+    return out
+
+
+def bench_v1_rollout(torch, dev, peak, N, n, K=ROLLOUT_K, reps=10):
+    """BASELINE.json configs[4] (5v5 at 2^18 envs) and its siblings: the v1 N-vs-N rigid-body variant, fused K = 64 rollouts
+    with given uniform random left-team actions (HBM resident), random right team drawn in-kernel."""
+    from gym_futbol_b200 import FutbolV1VecEnv
+    env = FutbolV1VecEnv(n, number_of_player=N, device=dev, seed=0)
+    env.reset()
+    acts = torch.randint(0, 5, (K, n, 2 * N), dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        env.rollout(K, actions=acts)
+    env.read_stats(clear=True)
+    ms = _timed(torch, lambda: env.rollout(K, actions=acts), reps)
+    st = env.read_stats()
+    B = 2 * N + 1
+    P = B * (B - 1) // 2 + 12 * B
+    state_bytes = 48 * B + 18                                     # bodies + scalars; the arbiter cache is touched only by contacts
+    bpe = (4 + 8 * N) * 4 + 4 + 1 + 2 * N + 2.0 * state_bytes / K
+    rate = n * K / (ms * 1e-3)
+    out = {"workload": "v1 Futbol %dv%d, %d envs, fused K=%d rollout, given random left actions" % (N, N, n, K), "launches_timed": reps,
+           "ms_per_launch": ms, "env_steps_per_s": rate, "bytes_per_env_step": bpe, "hbm_gbs": rate * bpe / 1e9,
+           "hbm_frac": rate * bpe / 1e9 / peak, "contacts_per_env_step": st["contacts"] / max(1, st["env_steps"]),
+           "contacts_dropped": st["contacts_dropped"], "arbiter_cache_bytes_per_env": 16 * P,
+           "note": "latency bound (sequential turns, Gauss-Seidel contact solver, divergent contacts): see profiles/r2_v1_history.md"}
+    env.close()
+    return out
+
+
+def bench_ppo(torch, dev, n=65536, T=128, iters=4):
+    """BASELINE.json configs[3]: PPO collection and collection + update at 65,536 envs (examples/ppo_v0.py), with the fused
+    glue (step(out=...) into the rollout buffers, one-launch minibatch gather) and, for the before/after, without."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ppo_v0", os.path.join(ROOT, "examples", "ppo_v0.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = {"workload": "PPO on v0 2v2 vs hard-coded opponents, %d envs, n_steps %d, 4 minibatches x 4 epochs, MLP [256,256]+[128,128] "
+                       "heads (bf16 autocast), collection replayed as one CUDA graph" % (n, T), "iterations_timed": iters}
+    for label, fused in (("fused", True), ("unfused", False)):
+        ppo = mod.PPO(n_envs=n, n_steps=T, seed=0, device=str(dev), fused=fused)
+        ppo.collect(); ppo.update()                      # eager warm-up iteration
+        ppo.prepare_graph()
+        ppo.collect(); ppo.update()
+        torch.cuda.synchronize()
+        c_ms = u_ms = 0.0
+        for _ in range(iters):
+            c_ms += _timed(torch, ppo.collect, 1)
+            u_ms += _timed(torch, ppo.update, 1)
+        out[label] = {"collect_env_steps_per_s": n * T * iters / (c_ms * 1e-3), "collect_ms": c_ms / iters,
+                      "collect_update_env_steps_per_s": n * T * iters / ((c_ms + u_ms) * 1e-3), "update_ms": u_ms / iters,
+                      "obs_zero_copy": True}
+        ppo.env.close()
+        del ppo
+        torch.cuda.empty_cache()
+    out["note"] = ("fused = the step kernel writes obs/reward/done into the rollout-buffer rows (no per-step copies) and one gather launch "
+                   "builds each minibatch; unfused = copy per step + six torch indexing launches per minibatch; the torch MLP is the cost")
+    return out
+
+
+def cpu_reference_baseline(budget_s=8.0):
+    """The UNMODIFIED Python reference FutbolEnv, SubprocVecEnv style over the host cores, timed in this same run."""
+    root = python_reference_available()
+    cores = os.cpu_count() or 1
+    if root is None:
+        return {"unavailable": "reference package not found (looked for baseline/_ref)"}
+    pool = PythonReferencePool(cores, 4, 1500)
+    pool.step()
+    t0, total = time.perf_counter(), 0
+    while time.perf_counter() - t0 < budget_s:
+        total += pool.step()
+    dt = time.perf_counter() - t0
+    pool.close()
+    return {"value": total / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": "unmodified reference FutbolEnv (%s), gym/matplotlib stand-ins + injected stdlib-MT RNG, random_opp=False; %d processes x 4 envs, "
+                      "%d env-steps in %.1f s" % (root, cores, total, dt)}
 
 
 if __name__ == "__main__":

@@ -13,6 +13,10 @@ using namespace futbol;
 
 namespace futbol {
 cudaError_t launch_selftest_arith(const double *a, const double *b, unsigned long long *mismatch, size_t n, cudaStream_t st);
+cudaError_t launch_gather_minibatch(const long long *idx, long long m, long long rows, const float *obs, int obs_dim, float *obs_out,
+                                    const uint8_t *act, uint8_t *act_out, const float *c0, float *c0_out, const float *c1,
+                                    float *c1_out, const float *c2, float *c2_out, const float *c3, float *c3_out,
+                                    unsigned long long *bad, cudaStream_t st);
 cudaError_t launch_gae(const float *reward, const uint8_t *done, const float *value, float gamma, float lam, float *adv,
                        float *ret, int T, int n, cudaStream_t st);
 }
@@ -102,11 +106,14 @@ int futbol_create(const FutbolConfig *cfg, FutbolHandle **out)
     if (cfg->variant != FUTBOL_VARIANT_V0 && !is_v1) return fail(FUTBOL_ERR_UNSUPPORTED, "unknown variant%s");
     if (!is_v1) {
         if (cfg->n_players != 2) return fail(FUTBOL_ERR_ARG, "v0 is 2v2: n_players must be 2%s");
-        if (!(cfg->game_time >= 0.0) || !(cfg->player_speed >= 0.0) || cfg->shoot_speed < 16)
-            return fail(FUTBOL_ERR_ARG, "bad game_time / player_speed / shoot_speed%s");
+        // upper bounds: the kernels' guard-free division / square root (csrc/ieee_fast.cuh) are proven for pitch-scale
+        // operands only, shoot_speed - 16 + r must not overflow, and the episode limit is found by repeated addition
+        if (!(cfg->game_time >= 0.0 && cfg->game_time <= 1e6) || !(cfg->player_speed >= 0.0 && cfg->player_speed <= 1e4) ||
+            cfg->shoot_speed < 16 || cfg->shoot_speed > 10000)
+            return fail(FUTBOL_ERR_ARG, "bad game_time (0..1e6) / player_speed (0..1e4) / shoot_speed (16..10000)%s");
     } else {
         if (cfg->n_players < 1 || cfg->n_players > v1::kMaxN) return fail(FUTBOL_ERR_ARG, "v1: n_players must be 1..10%s");
-        if (!(cfg->game_time >= 0.0)) return fail(FUTBOL_ERR_ARG, "bad total_time%s");
+        if (!(cfg->game_time >= 0.0 && cfg->game_time <= 1e6)) return fail(FUTBOL_ERR_ARG, "bad total_time (0..1e6)%s");
     }
     int dev_count = 0;
     cudaError_t e = cudaGetDeviceCount(&dev_count);
@@ -173,6 +180,12 @@ int futbol_act_dim(const FutbolHandle *h) { return h ? (h->is_v1 ? 2 * h->cfg.n_
 int futbol_draw_limit_steps(const FutbolHandle *h) { return h ? (h->is_v1 ? h->v1.ep_limit : h->v0.ep_limit + 1) : 0; }
 uint64_t futbol_launch_count(const FutbolHandle *h) { return h ? h->launches : 0; }
 
+int futbol_rollout_slices(FutbolHandle *h, int K)
+{
+    if (h == nullptr || K <= 0) return fail(FUTBOL_ERR_ARG, "null handle or K <= 0%s");
+    return h->is_v1 ? 1 : v0_rollout_slices(h->v0, K, h->rollout_slices);
+}
+
 int futbol_set_rollout_slices(FutbolHandle *h, int slices)
 {
     if (h == nullptr || slices < 0) return fail(FUTBOL_ERR_ARG, "null handle or negative slice count%s");
@@ -202,6 +215,7 @@ int futbol_step_vs(FutbolHandle *h, void *state, const uint8_t *actions, const u
     if (h == nullptr || state == nullptr || actions == nullptr) return fail(FUTBOL_ERR_ARG, "null handle/state/actions%s");
     if (out_dtype != 0 && out_dtype != 1) return fail(FUTBOL_ERR_ARG, "out_dtype must be 0 (f32) or 1 (f64)%s");
     if (!h->initialised) return fail(FUTBOL_ERR_ARG, "futbol_reset must be called before futbol_step%s");
+    if (h->is_v1 && ((uintptr_t)actions & 1u)) return fail(FUTBOL_ERR_ARG, "v1: the action buffer must be 2-byte aligned%s");
     cudaError_t e = h->is_v1 ? v1::launch_step(h->v1, state, actions, opp_actions, obs, reward, done, final_obs, out_dtype, (cudaStream_t)stream)
                              : v0_launch_step(h->v0, state, actions, opp_actions, obs, reward, done, final_obs, out_dtype, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
@@ -223,6 +237,7 @@ int futbol_rollout_vs(FutbolHandle *h, void *state, int K, const uint8_t *action
     if (h == nullptr || state == nullptr) return fail(FUTBOL_ERR_ARG, "null handle/state%s");
     if (K <= 0) return fail(FUTBOL_ERR_ARG, "K must be positive%s");
     if (!h->initialised) return fail(FUTBOL_ERR_ARG, "futbol_reset must be called before futbol_rollout%s");
+    if (h->is_v1 && ((uintptr_t)actions & 1u)) return fail(FUTBOL_ERR_ARG, "v1: the action buffer must be 2-byte aligned%s");
     cudaError_t e = h->is_v1 ? v1::launch_rollout(h->v1, state, K, actions, opp_actions, obs, reward, done, stats, (cudaStream_t)stream)
                              : v0_launch_rollout(h->v0, state, K, actions, opp_actions, obs, reward, done, stats, h->rollout_slices, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
@@ -243,6 +258,21 @@ int futbol_gae(const float *reward, const uint8_t *done, const float *value, flo
         return fail(FUTBOL_ERR_ARG, "null argument%s");
     if (T <= 0 || n <= 0) return fail(FUTBOL_ERR_ARG, "T and n must be positive%s");
     cudaError_t e = launch_gae(reward, done, value, gamma, lam, adv, ret, T, n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    return FUTBOL_OK;
+}
+
+int futbol_gather_minibatch(const int64_t *idx, int64_t m, int64_t rows, const float *obs, int obs_dim, float *obs_out,
+                            const uint8_t *act, uint8_t *act_out, const float *c0, float *c0_out, const float *c1, float *c1_out,
+                            const float *c2, float *c2_out, const float *c3, float *c3_out, uint64_t *bad, void *stream)
+{
+    if (idx == nullptr || m <= 0 || rows <= 0) return fail(FUTBOL_ERR_ARG, "null index or empty minibatch%s");
+    if ((obs != nullptr) != (obs_out != nullptr) || (act != nullptr) != (act_out != nullptr) || (c0 != nullptr) != (c0_out != nullptr) ||
+        (c1 != nullptr) != (c1_out != nullptr) || (c2 != nullptr) != (c2_out != nullptr) || (c3 != nullptr) != (c3_out != nullptr))
+        return fail(FUTBOL_ERR_ARG, "every source column needs its destination (and vice versa)%s");
+    if (obs != nullptr && obs_dim <= 0) return fail(FUTBOL_ERR_ARG, "obs_dim must be positive%s");
+    cudaError_t e = launch_gather_minibatch((const long long *)idx, m, rows, obs, obs_dim, obs_out, act, act_out, c0, c0_out, c1, c1_out,
+                                            c2, c2_out, c3, c3_out, (unsigned long long *)bad, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     return FUTBOL_OK;
 }

@@ -32,6 +32,50 @@ __global__ void __launch_bounds__(256) gae_kernel(const float *__restrict__ rewa
     }
 }
 
+// Minibatch gather: row idx[j] of every rollout-buffer column into row j of the minibatch, ONE pass over the index
+// (stable-baselines' runner slices its flattened [T * n] buffers per minibatch, colab_notebook.ipynb:852; on the device
+// that is six indexing launches that each re-read the permutation).  One warp per sample: lanes copy the observation
+// row (obs_dim floats, a contiguous run), the last lanes the action byte and up to four float scalars (old log-prob,
+// advantage, return, value).  HBM-bound: (4 obs_dim + 17) bytes read and written per sample + 8 of index.
+__global__ void __launch_bounds__(256) gather_minibatch_kernel(const long long *__restrict__ idx, long long m, long long rows,
+                                                               const float *__restrict__ obs, int obs_dim, float *__restrict__ obs_out,
+                                                               const uint8_t *__restrict__ act, uint8_t *__restrict__ act_out,
+                                                               const float *__restrict__ c0, float *__restrict__ c0_out,
+                                                               const float *__restrict__ c1, float *__restrict__ c1_out,
+                                                               const float *__restrict__ c2, float *__restrict__ c2_out,
+                                                               const float *__restrict__ c3, float *__restrict__ c3_out,
+                                                               unsigned long long *__restrict__ bad)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long j = warp; j < m; j += n_warps) {
+        const long long r = idx[j];
+        if (r < 0 || r >= rows) {                                 // never dereferenced: counted, the row is zero-filled
+            if (lane == 0 && bad != nullptr) atomicAdd(bad, 1ull);
+            if (obs != nullptr) for (int k = lane; k < obs_dim; k += 32) obs_out[j * obs_dim + k] = 0.0f;
+            continue;
+        }
+        if (obs != nullptr) for (int k = lane; k < obs_dim; k += 32) obs_out[j * obs_dim + k] = __ldg(obs + r * obs_dim + k);
+        if (lane == 31 && act != nullptr) act_out[j] = act[r];
+        if (lane == 30 && c0 != nullptr) c0_out[j] = c0[r];
+        if (lane == 29 && c1 != nullptr) c1_out[j] = c1[r];
+        if (lane == 28 && c2 != nullptr) c2_out[j] = c2[r];
+        if (lane == 27 && c3 != nullptr) c3_out[j] = c3[r];
+    }
+}
+
+cudaError_t launch_gather_minibatch(const long long *idx, long long m, long long rows, const float *obs, int obs_dim, float *obs_out,
+                                    const uint8_t *act, uint8_t *act_out, const float *c0, float *c0_out, const float *c1,
+                                    float *c1_out, const float *c2, float *c2_out, const float *c3, float *c3_out,
+                                    unsigned long long *bad, cudaStream_t st)
+{
+    long long blocks = (m + 7) / 8;                               // 8 warps per block, one sample per warp per trip
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    gather_minibatch_kernel<<<(int)blocks, 256, 0, st>>>(idx, m, rows, obs, obs_dim, obs_out, act, act_out, c0, c0_out, c1, c1_out,
+                                                         c2, c2_out, c3, c3_out, bad);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gae(const float *reward, const uint8_t *done, const float *value, float gamma, float lam, float *adv,
                        float *ret, int T, int n, cudaStream_t st)
 {

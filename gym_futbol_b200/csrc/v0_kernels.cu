@@ -11,6 +11,7 @@
 // = 223 bytes per env.  Inside a kernel the 25 doubles of an environment sit in shared memory (one column
 // per lane, v0_step.cuh) and the scalars in registers; HBM is touched at the two ends of a launch only.
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdint.h>
 #include "../../include/futbol_b200.h"
 #include "v0_step.cuh"
@@ -364,19 +365,45 @@ cudaError_t v0_launch_step(const V0Params &P, void *state, const uint8_t *action
     return cudaGetLastError();
 }
 
-// resident blocks of the rollout kernels on the current device (SMs x blocks per SM), queried once per variant
+// resident blocks of the rollout kernels on the CURRENT device (SMs x blocks per SM), queried once per device and variant
+// (a process may drive several GPUs, or create environments from several threads)
 template <bool RANDOM_OPP>
 static int rollout_block_slots()
 {
-    static int slots = 0;
-    if (slots == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
+    static std::mutex mu;
+    static int slots[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    int &s = slots[dev & 63];
+    if (s == 0) {
+        int sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v0_rollout_sliced_kernel<RANDOM_OPP>, kEnvThreads, kEnvSmemBytes);
-        slots = sms * per_sm > 0 ? sms * per_sm : 1;
+        s = sms * per_sm > 0 ? sms * per_sm : 1;
     }
-    return slots;
+    return s;
+}
+
+// Number of time slices a K-step rollout of this batch is cut into (1 = the plain kernel).
+// Plain launch when the batch is under one wave (nothing to balance) or many waves (the tail is a few percent).
+// In between, slice the K steps so that the queue holds five to six waves of units: each unit pays one state round
+// trip, and measured on a B200 (tools/time_rank_batch.py, K = 64) 4 slices are best for 131,072 envs (+18 % over
+// the plain launch), 2 for 262,144 (+3 %); finer slicing loses more to the round trips than the shorter tail gains.
+int v0_rollout_slices(const V0Params &P, int K, int slices)
+{
+    const int groups = blocks_for(P.n_envs, kEnvThreads);
+    const int slots = P.random_opp ? rollout_block_slots<true>() : rollout_block_slots<false>();
+    int chunks = 1;
+    if (slices > 0) chunks = slices < K ? slices : K;               // futbol_set_rollout_slices: tests, tuning
+    else if (groups > slots && groups < 6 * slots) {
+        chunks = (11 * slots + 2 * groups - 1) / (2 * groups);
+        if (chunks > K / 4) chunks = K / 4;
+    }
+    if (chunks < 1) chunks = 1;
+    if (chunks == 1) return 1;
+    const int chunk_steps = (K + chunks - 1) / chunks;
+    return (K + chunk_steps - 1) / chunk_steps;
 }
 
 template <bool RANDOM_OPP>
@@ -385,23 +412,12 @@ static cudaError_t launch_rollout(const V0Params &P, const StateView &v, int K, 
 {
     const int groups = blocks_for(P.n_envs, kEnvThreads);
     const int slots = rollout_block_slots<RANDOM_OPP>();
-    // Plain launch when the batch is under one wave (nothing to balance) or many waves (the tail is a few percent).
-    // In between, slice the K steps so that the queue holds five to six waves of units: each unit pays one state round
-    // trip, and measured on a B200 (tools/time_rank_batch.py, K = 64) 4 slices are best for 131,072 envs (+18 % over
-    // the plain launch), 2 for 262,144 (+3 %); finer slicing loses more to the round trips than the shorter tail gains.
-    int chunks = 1;
-    if (slices > 0) chunks = slices < K ? slices : K;               // futbol_set_rollout_slices: tests, tuning
-    else if (groups > slots && groups < 6 * slots) {
-        chunks = (11 * slots + 2 * groups - 1) / (2 * groups);
-        if (chunks > K / 4) chunks = K / 4;
-    }
-    if (chunks < 1) chunks = 1;
+    const int chunks = v0_rollout_slices(P, K, slices);
     if (chunks == 1) {
         v0_rollout_kernel<RANDOM_OPP><<<groups, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
         return cudaGetLastError();
     }
     const int chunk_steps = (K + chunks - 1) / chunks;
-    chunks = (K + chunk_steps - 1) / chunk_steps;
     cudaError_t e = cudaMemsetAsync(v.sched, 0, v0_sched_words(v.np) * 4, st);
     if (e != cudaSuccess) return e;
     const long long units = (long long)chunks * groups;

@@ -13,6 +13,7 @@ cudaError_t v0_launch_step(const V0Params &P, void *state, const uint8_t *action
                            void *reward, uint8_t *done, void *final_obs, int out_f64, cudaStream_t st);
 cudaError_t v0_launch_rollout(const V0Params &P, void *state, int K, const uint8_t *actions, const uint8_t *opp_actions,
                               float *obs, float *reward, uint8_t *done, FutbolStats *stats, int slices, cudaStream_t st);
+int v0_rollout_slices(const V0Params &P, int K, int slices);   // time slices the launcher will use (1 = plain kernel)
 cudaError_t v0_launch_get_state(int n, const void *state, void *aos, cudaStream_t st);
 cudaError_t v0_launch_set_state(int n, void *state, const void *aos, cudaStream_t st);
 }  // namespace futbol

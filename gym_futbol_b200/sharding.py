@@ -27,7 +27,12 @@ def allreduce_stats(stats: dict, group=None, device=None):
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return dict(stats)
-    t = torch.tensor([float(stats[k]) for k in STAT_KEYS], dtype=torch.float64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    out = {k: (float(v) if k == "reward_sum" else int(round(float(v)))) for k, v in zip(STAT_KEYS, t.tolist())}
+    # the integer counters are summed as integers (exact beyond 2**53); reward_sum in float64 (its last bits depend on the
+    # order of the device-side atomic adds and of this reduction)
+    counts = torch.tensor([int(stats[k]) for k in STAT_KEYS[1:]], dtype=torch.int64, device=device)
+    reward = torch.tensor([float(stats["reward_sum"])], dtype=torch.float64, device=device)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(reward, op=dist.ReduceOp.SUM, group=group)
+    out = {"reward_sum": float(reward.item())}
+    out.update({k: int(v) for k, v in zip(STAT_KEYS[1:], counts.tolist())})
     return out

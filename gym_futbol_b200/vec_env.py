@@ -93,6 +93,10 @@ class FutbolVecEnv:
     def launch_count(self):
         return int(self.lib.futbol_launch_count(self._h))
 
+    def rollout_slices(self, K):
+        """Number of time slices ``rollout(K)`` will use on this device (1 = the plain kernel)."""
+        return int(self.lib.futbol_rollout_slices(self._h, int(K)))
+
     def set_rollout_slices(self, slices):
         """Time slicing of ``rollout`` (include/futbol_b200.h): 0 = automatic, 1 = off, n = n slices.  Results are identical."""
         _lib.check(self.lib.futbol_set_rollout_slices(self._h, int(slices)))
@@ -100,6 +104,8 @@ class FutbolVecEnv:
     def _actions(self, actions, shape):
         if (type(actions) is torch.Tensor and actions.dtype == torch.uint8 and actions.device == self.device
                 and tuple(actions.shape) == shape and actions.is_contiguous()):
+            if self.act_shape and actions.data_ptr() & 1:     # v1 reads (arrow, key) pairs as 16-bit words: realign a view
+                return actions.clone()                        # that starts at an odd byte of a larger buffer
             return actions                                # the usual case: already what the kernel reads
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions), device=self.device)
@@ -119,19 +125,31 @@ class FutbolVecEnv:
             _lib.check(self.lib.futbol_reset(self._h, _ptr(self.state), _ptr(m), _ptr(self.obs), self._dt, self._stream()))
         return self.obs
 
-    def step(self, actions, opp_actions=None):
+    def step(self, actions, opp_actions=None, out=None):
         """actions: [n] ints in 0..15 (ai_1 = a // 4, ai_2 = a % 4).  opp_actions: None = the reference's own opponents;
-        else the opponents' actions in the same format (self-play / learned opponents; v0 needs random_opp=True)."""
+        else the opponents' actions in the same format (self-play / learned opponents; v0 needs random_opp=True).
+        out: None = this object's own buffers; else ``(obs, reward, done)`` -- contiguous CUDA tensors ``[n, obs_dim]`` /
+        ``[n]`` of this env's dtype / ``[n]`` uint8, e.g. row ``t`` of a PPO rollout buffer -- that the kernel writes
+        instead (no copy afterwards); an entry may be None (not written)."""
         if torch.cuda.current_device() != self._dev_index:
             with torch.cuda.device(self.device):
-                return self.step(actions, opp_actions)
+                return self.step(actions, opp_actions, out)
         a = self._actions(actions, self._step_shape)
         o = None if opp_actions is None else self._actions(opp_actions, self._step_shape).data_ptr()
         st, ob, rw, dn, fo = self._step_args
+        if out is not None:
+            obs_t, rew_t, done_t = out
+            n = self.num_envs
+            for t, shape, dt in ((obs_t, (n, self.obs_dim), self.dtype), (rew_t, (n,), self.dtype), (done_t, (n,), torch.uint8)):
+                if t is not None and (tuple(t.shape) != shape or t.dtype != dt or t.device != self.device or not t.is_contiguous()):
+                    raise ValueError("out tensors must be contiguous %s tensors of shape %s on %s" % (dt, shape, self.device))
+            ob, rw, dn = (None if t is None else t.data_ptr() for t in (obs_t, rew_t, done_t))
         rc = self.lib.futbol_step_vs(self._h, st, a.data_ptr(), o, ob, rw, dn, fo, self._dt,
                                      torch.cuda.current_stream().cuda_stream)
         if rc != 0:
             _lib.check(rc)
+        if out is not None:
+            return out[0], out[1], out[2], self._step_info
         return self.obs, self.rewards, self.dones, self._step_info
 
     def rollout(self, K, actions=None, obs=True, reward=True, done=True, out=None, opp_actions=None):

@@ -156,6 +156,16 @@ int futbol_set_state(FutbolHandle *h, void *state, const void *aos_in, void *str
 int futbol_gae(const float *reward, const uint8_t *done, const float *value, float gamma, float lam,
                float *adv, float *ret, int T, int n, void *stream);
 
+/* ---- rollout-buffer glue: minibatch gather ----------------------------------------------------
+ * Row idx[j] (int64, 0 <= idx[j] < rows) of every column of a flattened rollout buffer into row j of the minibatch, in
+ * ONE pass over the index: obs float32 [rows, obs_dim], act uint8 [rows], c0..c3 float32 [rows] (e.g. old log-prob,
+ * advantage, return, value).  Any column may be NULL together with its destination.  An out-of-range index is never
+ * dereferenced: its observation row is zero-filled and, when `bad` is not NULL, the device counter *bad is incremented.
+ * Replaces the per-minibatch slicing of stable-baselines' runner (colab_notebook.ipynb:852).  No handle. */
+int futbol_gather_minibatch(const int64_t *idx, int64_t m, int64_t rows, const float *obs, int obs_dim, float *obs_out,
+                            const uint8_t *act, uint8_t *act_out, const float *c0, float *c0_out, const float *c1, float *c1_out,
+                            const float *c2, float *c2_out, const float *c3, float *c3_out, uint64_t *bad, void *stream);
+
 /* ---- self test ----------------------------------------------------------------------------
  * Compares the kernel's guard-free fp64 division / square-root sequences (csrc/ieee_fast.cuh) with the
  * compiler's __ddiv_rn / __dsqrt_rn on n operand pairs: a[i] / b[i], (a[i], |b[i]|) / b[i] through the
@@ -173,6 +183,8 @@ uint64_t futbol_launch_count(const FutbolHandle *h);
  * launch from the batch size (default), 1 = never slice, n > 1 = n slices.  v0 only; ignored for v1.  No reference
  * counterpart. */
 int futbol_set_rollout_slices(FutbolHandle *h, int slices);
+/* the number of time slices futbol_rollout will use for K steps on the current device (1 = the plain kernel) */
+int futbol_rollout_slices(FutbolHandle *h, int K);
 
 #ifdef __cplusplus
 }

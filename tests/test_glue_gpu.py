@@ -90,3 +90,105 @@ def test_replay_of_a_rollout_buffer(torch_cuda, tmp_path):
     assert np.array_equal(t["ball"], o[:, 20:22]) and np.array_equal(t["team_b"][:, 1], o[:, 15:17])
     assert ((t["owner"] >= 0) & (t["owner"] <= 4)).all()
     assert save_gif(str(tmp_path / "r.gif"), t, scale=3) == K
+
+
+def test_step_writes_into_caller_buffers(torch_cuda):
+    """step(out=...) makes the kernel write observation / reward / done straight into rows of a rollout buffer: same
+    values as the env's own buffers would hold, which are left untouched; bad destinations are refused."""
+    from gym_futbol_b200 import FutbolV1VecEnv, FutbolVecEnv
+    torch = torch_cuda
+    for make, hi, D in ((lambda: FutbolVecEnv(300, seed=4, random_opp=False), 16, 30),
+                        (lambda: FutbolV1VecEnv(300, number_of_player=2, seed=4), 5, 20)):
+        a_env, b_env = make(), make()
+        a_env.reset(); b_env.reset()
+        n, T = 300, 12
+        obs_buf = torch.full((T + 1, n, D), -7.0, device="cuda")
+        rew_buf, done_buf = torch.zeros((T, n), device="cuda"), torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+        own = b_env.obs.clone()
+        g = torch.Generator(device="cuda").manual_seed(0)
+        for t in range(T):
+            act = torch.randint(0, hi, (n,) + tuple(a_env.act_shape), dtype=torch.uint8, device="cuda", generator=g)
+            o, r, d, _ = a_env.step(act)
+            o2, r2, d2, _ = b_env.step(act, out=(obs_buf[t + 1], rew_buf[t], done_buf[t]))
+            assert o2.data_ptr() == obs_buf[t + 1].data_ptr()
+            assert torch.equal(o, obs_buf[t + 1]) and torch.equal(r, rew_buf[t]) and torch.equal(d, done_buf[t])
+        assert torch.equal(b_env.obs, own)                      # the env's own observation buffer was not written
+        assert (obs_buf[0] == -7.0).all()
+        with pytest.raises(ValueError):
+            b_env.step(act, out=(obs_buf[:, :, 0], rew_buf[0], done_buf[0]))
+        with pytest.raises(ValueError):
+            b_env.step(act, out=(obs_buf[1], rew_buf[0].double(), done_buf[0]))
+        o3, r3, d3, _ = b_env.step(act, out=(None, rew_buf[0], None))     # entries may be None
+        assert o3 is None and d3 is None
+
+
+def test_gather_minibatch_equals_torch_indexing(torch_cuda):
+    from gym_futbol_b200 import rollout_buffer
+    torch = torch_cuda
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for T, n, D, m in ((16, 257, 30, 1031), (8, 64, 44, 512), (4, 33, 12, 132), (128, 4096, 30, 131072)):
+        obs = torch.randn((T, n, D), device="cuda", generator=g)
+        act = torch.randint(0, 16, (T, n), dtype=torch.uint8, device="cuda", generator=g)
+        cols = [torch.randn((T, n), device="cuda", generator=g) for _ in range(4)]
+        idx = torch.randperm(T * n, device="cuda", generator=g)[:m]
+        got = rollout_buffer.gather_minibatch(obs, idx, act=act, cols=cols)
+        want = [obs.view(T * n, D)[idx], act.view(-1)[idx]] + [c.view(-1)[idx] for c in cols]
+        assert len(got) == 6 and all(torch.equal(a, b) for a, b in zip(got, want))
+        only = rollout_buffer.gather_minibatch(obs, idx)
+        assert torch.equal(only, want[0])
+        dst = (torch.empty((m, D), device="cuda"), torch.empty(m, dtype=torch.uint8, device="cuda"), torch.empty(m, device="cuda"))
+        out = rollout_buffer.gather_minibatch(obs, idx, act=act, cols=cols[:1], out=dst)
+        assert out[0].data_ptr() == dst[0].data_ptr() and torch.equal(dst[0], want[0]) and torch.equal(dst[2], want[2])
+    with pytest.raises(ValueError):
+        rollout_buffer.gather_minibatch(obs, idx.int())
+    with pytest.raises(ValueError):
+        rollout_buffer.gather_minibatch(obs, idx, cols=cols + cols)
+
+
+def test_ppo_example_fused_equals_unfused(torch_cuda):
+    """configs[3] in small: the fused flow (step(out=...) + one-launch gather) computes what the copy / indexing flow
+    computes -- same rollout buffers after collection, and a finite loss after an update."""
+    import importlib.util
+    import os
+    torch = torch_cuda
+    spec = importlib.util.spec_from_file_location("ppo_v0", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "ppo_v0.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    runs = []
+    for fused in (True, False):
+        ppo = mod.PPO(n_envs=512, n_steps=16, minibatches=2, epochs=1, seed=1, bf16=False, fused=fused, graph=False)
+        torch.manual_seed(5)
+        ppo.collect()
+        ppo.collect()                                          # the second collection continues from the first
+        torch.cuda.synchronize()
+        runs.append([t.clone() for t in (ppo.obs_buf[:16], ppo.act_buf, ppo.rew_buf, ppo.done_buf, ppo.adv, ppo.ret)])
+        ppo.update()
+        assert torch.isfinite(ppo.last_loss).item()
+    assert all(torch.equal(a, b) for a, b in zip(*runs))
+
+
+def test_host_rollout_delivers_the_device_rollout(torch_cuda):
+    """gym_futbol_b200.host_io.HostRollout (bench.py's e2e path): pinned-host actions in, every observation / reward / done
+    of the K steps in pinned host memory -- the same bytes a device-resident rollout with those actions produces."""
+    from gym_futbol_b200 import FutbolV1VecEnv, FutbolVecEnv, host_io
+    torch = torch_cuda
+    for make, hi in ((lambda: FutbolVecEnv(1000, seed=8, random_opp=False), 16), (lambda: FutbolV1VecEnv(333, number_of_player=2, seed=8), 5)):
+        a_env, b_env = make(), make()
+        a_env.reset(); b_env.reset()
+        K = 32
+        pipe = host_io.HostRollout(b_env, K, chunks=4)
+        assert pipe.h_obs.is_pinned() and pipe.h_actions.is_pinned()
+        pipe.h_actions.copy_(torch.randint(0, hi, tuple(pipe.h_actions.shape), dtype=torch.uint8))
+        for rep in range(2):
+            want = a_env.rollout(K, actions=pipe.h_actions.cuda())
+            h_obs, h_rew, h_done = pipe.run()
+            assert torch.equal(h_obs, want[0].cpu()) and torch.equal(h_rew, want[1].cpu()) and torch.equal(h_done, want[2].cpu())
+        assert pipe.d2h_bytes == K * b_env.num_envs * (b_env.obs_dim * 4 + 5) + 64 and pipe.h2d_bytes == pipe.h_actions.numel()
+        pipe.run_resident()
+        a_env.rollout(K, actions=pipe.h_actions.cuda())
+        assert a_env.get_state().tobytes() == b_env.get_state().tobytes()
+    with pytest.raises(ValueError):
+        host_io.HostRollout(b_env, 30, chunks=4)
+    assert host_io.measure_d2h_peak("cuda:0", nbytes=1 << 24, reps=1) > 0.1
+    cpus = host_io.gpu_local_cpus(0)
+    assert cpus is None or len(cpus) >= 1
