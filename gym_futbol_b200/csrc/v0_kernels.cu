@@ -81,6 +81,29 @@ __device__ __forceinline__ void store_state(const StateView &v, int i, Lane L, c
 // per instruction.  fp32 rows are therefore staged through shared memory per warp and written out as
 // consecutive 128-bit stores (a warp's 32 rows are one contiguous 3840-byte span of [n, 30]).  The
 // staging area reuses the space of the step's draw words (dead by now), hence the leading __syncwarp.
+// Bulk asynchronous copy shared -> global (cp.async.bulk, SASS UBLKCP): one lane hands the warp's finished 3840-byte tile to
+// the copy engine instead of 32 lanes moving it with 8 LDS.128 + 8 STG.128 each.  The staging area may be rewritten (by
+// the next step's draw words) only after the engine has READ it: bulk_wait_read() before that.
+// Measured (2^20 envs, K = 64, profiles/r2_v0_history.md): +1.4 % with random opponents (1.221 -> 1.238e10 env-steps/s),
+// -6.7 % with the hard-coded opponents (1.056 -> 0.985e10; the larger kernel, instruction-fetch bound), so only the
+// random-opponent kernels use it.
+#ifndef FUTBOL_NO_BULK_STORE
+#define FUTBOL_BULK_STORE 1
+#else
+#define FUTBOL_BULK_STORE 0
+#endif
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// BULK: the tile leaves through the copy engine when it is a whole, 16-byte aligned warp tile (the rollout kernels, which
+// call bulk_wait_read() before the staging area is reused); otherwise, and in the per-step kernel, through the lanes.
+template <bool BULK = false>
 __device__ __forceinline__ void warp_store_obs_f32(Lane L, const V0Regs &s, float *stage, float *gdst_warp_row0,
                                                    int lane, int rows_in_warp, bool vec_ok)
 {
@@ -98,6 +121,12 @@ __device__ __forceinline__ void warp_store_obs_f32(Lane L, const V0Regs &s, floa
     }
 #pragma unroll
     for (int k = 0; k < 5; ++k) mine[25 + k] = (float)obs_owner_elem(s, k);
+    if (BULK && FUTBOL_BULK_STORE && vec_ok && rows_in_warp == 32) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // this lane's staged values -> visible to the async proxy
+        __syncwarp();
+        if (lane == 0) bulk_store_s2g(gdst_warp_row0, stage, 32 * kObsDim * 4);
+        return;
+    }
     __syncwarp();
     const int total = rows_in_warp * kObsDim;
     if (vec_ok) {
@@ -204,6 +233,7 @@ __device__ __forceinline__ void rollout_span(const V0Params &P, const StateView 
     const uint32_t env_id = P.env_id_offset + (uint32_t)i;
     const Lane L = make_lane(warp, lane);
     float *stage = reinterpret_cast<float *>(futbol_smem + warp * kWarpSmemBytes + kWarpStateBytes);
+    constexpr bool kBulk = FUTBOL_BULK_STORE && RANDOM_OPP;
 
     V0Regs s;
     if (live) load_state(v, i, L, s);
@@ -224,7 +254,14 @@ __device__ __forceinline__ void rollout_span(const V0Params &P, const StateView 
         } else a = philox_action(P.key, env_id, s.t_total, 16);
         const int ai_before = s.ai_score;
         const int oa = (opp_actions != nullptr && live) ? (int)(__ldg(opp_actions + slot) & 15) : -1;
-        const StepResult r = v0_step<RANDOM_OPP>(L, s, P, env_id, a, oa);
+        // the draw words are parked where the previous step's observation tile was staged: with the bulk store, wait (after
+        // the Philox arithmetic, in registers) until the copy engine has read that tile
+        const bool wait_tile = kBulk && obs != nullptr && k > k0;
+        const StepResult r = v0_step<RANDOM_OPP>(L, s, P, env_id, a, oa, [&]() {
+            if (kBulk) {
+                if (wait_tile) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
+            }
+        });
         last_flags = r.flags;
         reward_sum += r.reward;
         goals_ai += (r.flags & kFlagGoal) && s.ai_score != ai_before;
@@ -233,13 +270,14 @@ __device__ __forceinline__ void rollout_span(const V0Params &P, const StateView 
         episodes += r.done;
         if (r.done && P.auto_reset) reset_env(L, s);
         if (obs != nullptr)
-            warp_store_obs_f32(L, s, stage, obs + ((size_t)k * n + (size_t)warp_env0) * kObsDim, lane, rows_in_warp, vec_ok);
+            warp_store_obs_f32<kBulk>(L, s, stage, obs + ((size_t)k * n + (size_t)warp_env0) * kObsDim, lane, rows_in_warp, vec_ok);
         if (live) {
             if (reward != nullptr) __stcs(reward + slot, (float)r.reward);
             if (done != nullptr) done[slot] = (uint8_t)r.done;
         }
     }
     if (live) store_state(v, i, L, s, last_flags);
+    if (kBulk && obs != nullptr && lane == 0) bulk_wait_all();                  // every tile of this span has landed
 
     if (stats != nullptr) {
         if (!live) { reward_sum = 0.0; episodes = goals_ai = goals_opp = fixes = 0; }

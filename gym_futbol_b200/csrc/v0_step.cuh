@@ -45,9 +45,11 @@ constexpr double kNaN = __builtin_nan("");
 //   d > 12.0  <=>  s >  144.0
 // (sqrt(s) rounds to c or below exactly when it lies below the midpoint of c and its successor; squaring
 // that midpoint gives the bound.  tests/test_sqrt_thresholds.py checks every neighbouring double.)
+//   d <  1.0  <=>  s <  1.0          d <  4.0  <=>  s <  16.0      (the predecessor of c*c has a root below c)
 constexpr double kSqLe1 = 0x1.0000000000001p+0;
 constexpr double kSqLe2 = 0x1.0000000000001p+2;
 constexpr double kSqGt12 = 144.0;
+constexpr double kSqLt1 = 1.0, kSqLt4 = 16.0;
 // products of reference constants, rounded once as the reference's float64 multiply rounds them
 // (__dmul_rn is not folded by the compiler; tests/test_sqrt_thresholds.py::test_constant_products)
 constexpr double kWid02 = 13.600000000000001;   // width * 0.2, :895
@@ -216,7 +218,10 @@ __device__ __forceinline__ void reset_env(Lane L, V0Regs &s)
 // last player turn: everything it reads (player and ball POSITIONS) only changes in the kinematics
 // phase, and the vector it writes is first read there.  A later successful intercept overwrites the
 // whole ball row (:465-466), which cancels the pending kick.
-struct PendingShot { int shooter; int target_y; uint32_t pick_idx; };
+// The same holds for a pass (assist): it needs the ball too, so a step has at most ONE pending kick of either kind.  The
+// pass's speed (|mate - ball| / 0.1 capped at 20, +- 1 uniform, :413-416: a square root and a division) is resolved at that
+// same site from the positions, which do not change before the kinematics phase, and the draw taken at the turn.
+struct PendingShot { int shooter; int target_y; uint32_t pick_idx; int passer; uint32_t pass_w; };
 
 // Draw budget of a step (sequential draws; the kick's normal() slots are addressed separately).  In turn
 // order: [random_opp: 1 | hard-coded: <= 1, only the opponent holding the ball can draw in get_action_type],
@@ -247,24 +252,16 @@ __device__ __forceinline__ void player_turn(Lane L, uint32_t &j, V0Regs &s, cons
     const double bx = dsub(ball_x, ax), by = dsub(ball_y, ay);           // :432
     const double vx = hb_assist ? dsub(mx, ball_x) : bx;                 // :412
     const double vy = hb_assist ? dsub(my, ball_y) : by;
-    // The one magnitude a turn needs (no-ball intercept: |ball - player|; has-ball assist: |mate - ball|).
-    // sqrt(0) and 0/x leave the fast path of the IEEE sequences (a subroutine call for the lanes that
-    // hold the ball, whose ball-player vector is exactly zero), so those lanes are fed a benign operand
-    // and the exact result (0) is selected afterwards.
-    const double q = sqsum(vx, vy);
-    const bool q_zero = q == 0.0;
-    const double root = fsqrt(pick((nb_int || hb_assist) && !q_zero, q, 1.0));
-    const double mag = q_zero ? 0.0 : root;
-
-    // has-ball assist, :413-416
-    const double quot = fdiv(pick(hb_assist && !q_zero, mag, 1.0), kStepSize);
-    double pass = q_zero ? 0.0 : quot;
-    pass = pass > 20.0 ? 20.0 : pass;
-    const double lo = dsub(pass, 1.0), hi = dadd(pass, 1.0);
-    const double pass_speed = dadd(lo, dmul(dsub(hi, lo), u));           // random.uniform
-    // no-ball intercept, :452-463; intercept_chance(d, 1, 2) :122-129 with k = 0.9 / (1 - 2) = -0.9 exactly
-    const double chance = mag < 1.0 ? 0.9 : (mag <= 2.0 ? dmul(-0.9, dsub(mag, 2.0)) : 0.0);
-    const bool take = nb_int && (u < chance || (s.owner == kNoOne && mag < 4.0));
+    // no-ball intercept, :452-463: intercept_chance(d, 1, 2) (:122-129, k = 0.9 / (1 - 2) = -0.9 exactly) is 0.9 below 1,
+    // 0 above 2, and an unowned ball within 4 is taken whatever the chance: all decided on the SQUARED distance (exact
+    // bounds above).  The root itself is needed only for an owned ball at 1 <= d <= 2 -- about one turn in a hundred --
+    // and is taken behind a branch that most warps skip (it was a full sqrt per player per step: ~45 instructions).
+    const double q = sqsum(bx, by);
+    const bool lt1 = q < kSqLt1, le2 = q <= kSqLe2, free_ball = s.owner == kNoOne;
+    const bool mid = nb_int && !lt1 && le2 && !free_ball;
+    double chance_mid = 0.0;
+    if (mid) chance_mid = dmul(-0.9, dsub(fsqrt(q), 2.0));               // q in [1, 4]: inside the guard-free sqrt's domain
+    const bool take = nb_int && ((free_ball && q < kSqLt4) || (lt1 ? u < 0.9 : (mid && u < chance_mid)));
     // has-ball run, :353-356 (Q3)
     const bool drop = hb_run && u < 0.05;
     const bool carry = hb_run && !drop;
@@ -283,13 +280,14 @@ __device__ __forceinline__ void player_turn(Lane L, uint32_t &j, V0Regs &s, cons
         L.f(bo + kTX) = hb_int ? 0.0 : (hb_assist ? vx : rtx);
         L.f(bo + kTY) = hb_int ? 0.0 : (hb_assist ? vy : rty);
     }
-    if (carry || take || hb_int || hb_assist || hb_shoot) {              // :367 kick speed; vector resolved later
+    if (carry || take || hb_int || hb_shoot) {                           // :367 kick speed; the vector (and a pass's speed) are resolved later
         const double kick = (double)(P.shoot_speed - 16 + (int)__umulhi(w, 17u));
-        L.f(bo + kSP) = hb_int ? 0.0 : (hb_assist ? pass_speed : (hb_shoot ? kick : rsp));
+        L.f(bo + kSP) = hb_int ? 0.0 : (hb_shoot ? kick : rsp);
     }
     if (hb_shoot) { shot.shooter = a; shot.target_y = target_y; shot.pick_idx = j; }
+    if (hb_assist) { shot.passer = a; shot.pass_w = w; }
     j += hb_shoot ? 1u : 0u;                                             // randint(0, 9) of screw_vec, :107
-    if (take) shot.shooter = -1;
+    if (take) { shot.shooter = -1; shot.passer = -1; }
     if (hb_shoot || hb_assist || take) s.last_owner = s.owner;           // :381, :421, :467
     s.owner = take ? a : ((drop || hb_shoot || hb_assist) ? (int)kNoOne : s.owner);   // :354, :382, :422, :468
 }
@@ -340,6 +338,21 @@ __device__ __forceinline__ void resolve_shot(Lane L, const V0Regs &s, const V0Pa
     const double ts = dadd(dmul(sn, sc), dmul(c, ss));                   // :114
     L.f(bo + kTX) = dmul(tc, mag);                                       // :115
     L.f(bo + kTY) = dmul(ts, mag);
+}
+
+// the pending pass: ball speed = uniform(s - 1, s + 1), s = min(|mate - ball| / 0.1, 20), :413-416
+__device__ __forceinline__ void resolve_pass(Lane L, const PendingShot &shot)
+{
+    const int mo = (shot.passer ^ 1) * kRowStride, bo = kBallRow * kRowStride;
+    const double q = sqsum(dsub(L.f(mo + kX), L.f(bo + kX)), dsub(L.f(mo + kY), L.f(bo + kY)));
+    const bool q_zero = q == 0.0;                                        // mate on the ball: sqrt(0) / 0.1 = 0 as in the reference
+    const double mag = fsqrt(pick(!q_zero, q, 1.0));
+    const double quot = fdiv(pick(!q_zero, mag, 1.0), kStepSize);
+    double pass = q_zero ? 0.0 : quot;
+    pass = pass > 20.0 ? 20.0 : pass;
+    const double lo = dsub(pass, 1.0), hi = dadd(pass, 1.0);
+    const double u = (double)(shot.pass_w >> 8) * (1.0 / 16777216.0);
+    L.f(bo + kSP) = dadd(lo, dmul(dsub(hi, lo), u));                     // random.uniform
 }
 
 // Easy_Agent.get_action_type for 'right' opponent `a`, easy_agent.py:53-98
@@ -412,13 +425,18 @@ struct StepResult { double reward; int done; int flags; };
 // `opp_action`: -1 = the reference's own opponents; 0..15 (RANDOM_OPP variant only) = actions supplied by the caller
 // for opp_1 (a / 4) and opp_2 (a % 4), the self-play hook: same path as the random opponents (:642-645), the
 // randint(0, 15) draw is not taken.
-template <bool RANDOM_OPP>
-__device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params &P, uint32_t env_id, int ai_action, int opp_action = -1)
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+template <bool RANDOM_OPP, typename Hook = NoHook>
+__device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params &P, uint32_t env_id, int ai_action, int opp_action = -1,
+                                              Hook before_draw_store = Hook())
 {
-    philox_fill_step(&L.draw(0), P.key, env_id, kStreamDynamics, s.t_total);
+    // Two Philox blocks = the first eight sequential draws up front; the third block (draws 9 and 10) only when the last
+    // turn is about to consume one of them: never with the hard-coded opponents in 5,400 reference steps, 1.2 % of the
+    // steps with random ones (draw counts of tests/golden/v0_golden.npz), against 52 instructions on every step.
+    philox_fill_two(&L.draw(0), P.key, env_id, kStreamDynamics, s.t_total, before_draw_store);
     uint32_t j = 0;
     PendingShot shot;
-    shot.shooter = -1; shot.target_y = 0; shot.pick_idx = 0;
+    shot.shooter = -1; shot.target_y = 0; shot.pick_idx = 0; shot.passer = -1; shot.pass_w = 0;
     const int bo = kBallRow * kRowStride;
 
     // pre-step snapshot used by the reward (:630-635).  The owner one-hot row of the observation is all
@@ -477,6 +495,13 @@ __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params 
         const bool has_ball = latched ? (t == 0 ? has1 : has2) : s.owner == a;
         const int action = t == 0 ? opp_a1 : (t == 1 ? opp_a2 : (t == 2 ? action1 : action2));
         const bool set_target = latched && (t == 0 ? set1 : set2);
+        // Draws 9 and 10 (words 8 and 9) can only be consumed by the LAST turn: before turn 2 at most 1 + 3 + 2 = 6 draws
+        // are gone, and only after a shot (no second one can follow), so turn 2 ends at word 7.  The last turn consumes
+        // word j, word j + 1 when it draws (has-ball run / shoot / assist, no-ball intercept) and word j + 2 when it shoots.
+        if (t == 3) {
+            if (j + ((has_ball != (action == kIntercept)) ? 1u : 0u) + ((has_ball && action == kShoot) ? 1u : 0u) >= 8u)
+                philox_fill_block(&L.draw(0), P.key, env_id, kStreamDynamics, s.t_total, 2);
+        }
         player_turn(L, j, s, P, a, has_ball, action, set_target, t == 0 ? t1x : t2x, t == 0 ? t1y : t2y, shot);
         if (!RANDOM_OPP && t == 1) {
             // :962-982 anticipate the ball: whoever can reach its next position lands exactly on it
@@ -498,7 +523,10 @@ __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params 
             }
         }
     }
-    if (shot.shooter >= 0) resolve_shot(L, s, P, RANDOM_OPP, env_id, shot);
+    if ((shot.shooter & shot.passer) >= 0) {                             // at most one of the two is pending (both -1: skip)
+        if (shot.shooter >= 0) resolve_shot(L, s, P, RANDOM_OPP, env_id, shot);
+        else resolve_pass(L, shot);
+    }
 
     // ---- kinematics, :661-663 ----
     advance_all(L);

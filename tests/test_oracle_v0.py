@@ -170,3 +170,56 @@ def test_libm_mode_vs_kernel_mode_divergence_is_knife_edge_only():
             if first[i] > 0:
                 assert err[first[i] - 1, i] <= 1e-9, (i, first[i])
         assert err[:, ~diverged].max() <= 1e-7   # (bimodal: measured <= 3e-9 for these, O(1) for the split ones)
+
+
+def _wide():
+    import json
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "v0_wide_golden.npz"))
+    return {c: dict({k.split("/")[1]: z[k] for k in z.files if k.startswith(c + "/") and not k.endswith("meta")},
+                    meta=json.loads(str(z[c + "/meta"]))) for c in ("ro0", "ro1")}
+
+
+def wide_split_report(got, case):
+    """Per (env, episode): does any integer output of the episode differ from the reference's?  -> (split episodes, episodes,
+    mismatching env-steps)."""
+    mism = np.zeros(case["done"].shape, bool)
+    for f in INT_FIELDS:
+        mism |= got[f].astype(np.int64) != case[f].astype(np.int64)
+    ends = np.flatnonzero(case["done"][:, 0])            # the time limit: the same steps for every env
+    bounds = [0] + [int(e) + 1 for e in ends] + ([mism.shape[0]] if (not len(ends) or ends[-1] + 1 < mism.shape[0]) else [])
+    split = sum(int(mism[a:b].any(0).sum()) for a, b in zip(bounds[:-1], bounds[1:]))
+    return split, (len(bounds) - 1) * mism.shape[1], int(mism.sum())
+
+
+def test_wide_reference_set_libm_mode_is_exact(golden_v0):
+    """128,000 steps of the unmodified reference (64 envs x 1000 steps x both opponent modes, tests/golden/
+    make_golden_v0_wide.py): the oracle in libm mode reproduces every integer of every step, the draw counts, the rewards
+    and (same libm) the last observation bit for bit."""
+    for name, case in _wide().items():
+        m = case["meta"]
+        o = OracleV0(m["envs"], seed=m["seed"], env_id0=m["env_id0"], random_opp=m["random_opp"], arith=1)
+        out = o.rollout(m["steps"], actions=case["action"], autoreset=1, n_threads=8)
+        for f in INT_FIELDS:
+            assert np.array_equal(out[f].astype(np.int64), case[f].astype(np.int64)), (name, f)
+        draws = np.diff(np.concatenate([np.zeros((1, m["envs"]), np.uint64), out["draws"]]).astype(np.int64), axis=0)
+        assert np.array_equal(draws, case["draws"].astype(np.int64)), name
+        assert np.array_equal(out["reward"].astype(np.float32), case["reward"]), name
+        if golden_v0["same_libm"]:
+            assert np.array_equal(out["obs"][-1].reshape(-1, 6, 5), case["obs_last"]), name
+
+
+def test_wide_reference_set_kernel_arithmetic_split_rate():
+    """Kernel arithmetic (x*x for numpy-scalar x**2) against the same 128,000 reference steps: an episode may leave the
+    reference's at a last-bit compare.  Measured here: 0 of 192 episodes with random opponents, 2 of 192 with the
+    hard-coded ones; the bound is 6 % of the episodes, and every episode re-joins the reference at its reset."""
+    for name, case in _wide().items():
+        m = case["meta"]
+        o = OracleV0(m["envs"], seed=m["seed"], env_id0=m["env_id0"], random_opp=m["random_opp"], arith=0)
+        out = o.rollout(m["steps"], actions=case["action"], autoreset=1, n_threads=8)
+        split, episodes, steps = wide_split_report(out, case)
+        print("v0 wide %s: %d of %d episodes split (%d of %d env-steps differ)" % (name, split, episodes, steps, case["done"].size))
+        assert split <= 0.06 * episodes, (name, split, episodes)
+        first = np.flatnonzero(case["done"][:, 0])[0] + 1           # the first step of the second episode: all envs agree again
+        for f in ("owner", "last_owner", "ai_score", "opp_score"):
+            assert np.array_equal(out[f][first].astype(np.int64), case[f][first].astype(np.int64)), (name, f)

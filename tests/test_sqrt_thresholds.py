@@ -30,6 +30,17 @@ def test_fixed_thresholds():
         assert (math.sqrt(s) > 2.0) == (s > le2)
     for s in neighbours(144.0):
         assert (math.sqrt(s) > 12.0) == (s > 144.0)
+    # strict bounds of the intercept rule (v0_step.cuh kSqLt1 / kSqLt4): d < 1 <=> s < 1, d < 4 <=> s < 16
+    for s in neighbours(1.0):
+        assert (math.sqrt(s) < 1.0) == (s < 1.0)
+    for s in neighbours(16.0):
+        assert (math.sqrt(s) < 4.0) == (s < 16.0)
+    # v1 speed clamps (v1_step.cuh clamp_sq_*): sqrt(s) > max <=> s > largest s whose root is <= max
+    for mx in (10.0, 25.0):
+        from tests.test_v0_step_host import sqrt_less_than_bound
+        bound = sqrt_less_than_bound(math.nextafter(mx, math.inf))
+        for s in neighbours(bound) + neighbours(mx * mx):
+            assert (math.sqrt(s) > mx) == (s > bound)
 
 
 def test_reach_bound_for_many_speeds():
