@@ -55,7 +55,8 @@ EXPORTS = ("futbol_create", "futbol_destroy", "futbol_last_error", "futbol_abi_v
            "futbol_obs_dim", "futbol_act_dim", "futbol_draw_limit_steps", "futbol_reset", "futbol_step",
            "futbol_rollout", "futbol_env_state_bytes", "futbol_get_state", "futbol_set_state",
            "futbol_launch_count", "futbol_gae", "futbol_selftest_arith", "futbol_step_vs", "futbol_rollout_vs",
-           "futbol_set_rollout_slices", "futbol_rollout_slices", "futbol_gather_minibatch")
+           "futbol_set_rollout_slices", "futbol_rollout_slices", "futbol_rollout_kernel",
+           "futbol_set_rollout_variant", "futbol_gather_minibatch")
 
 _lib = None
 
@@ -107,6 +108,10 @@ def load():
     L.futbol_set_rollout_slices.argtypes = [vp, C.c_int]
     L.futbol_rollout_slices.restype = C.c_int
     L.futbol_rollout_slices.argtypes = [vp, C.c_int]
+    L.futbol_rollout_kernel.restype = C.c_int
+    L.futbol_rollout_kernel.argtypes = [vp, C.c_int]
+    L.futbol_set_rollout_variant.restype = C.c_int
+    L.futbol_set_rollout_variant.argtypes = [vp, C.c_int]
     L.futbol_gather_minibatch.restype = C.c_int
     L.futbol_gather_minibatch.argtypes = [vp, C.c_int64, C.c_int64, vp, C.c_int, vp] + [vp] * 10 + [vp, vp]
     L.futbol_launch_count.restype = C.c_uint64

@@ -29,6 +29,7 @@ struct FutbolHandle {
     uint64_t launches;
     bool initialised;   // first futbol_reset zeroes t_total
     int rollout_slices; // 0 = chosen per launch from the batch size (v0_kernels.cu)
+    int rollout_variant; // 0 = automatic, 1 = standard kernel, 2 = dense kernel (futbol_set_rollout_variant)
 };
 
 static thread_local char g_err[256] = "";
@@ -125,6 +126,7 @@ int futbol_create(const FutbolConfig *cfg, FutbolHandle **out)
     h->launches = 0;
     h->initialised = false;
     h->rollout_slices = 0;
+    h->rollout_variant = 0;
     h->is_v1 = is_v1;
     if (is_v1) {
         v1::V1Params &Q = h->v1;
@@ -183,7 +185,22 @@ uint64_t futbol_launch_count(const FutbolHandle *h) { return h ? h->launches : 0
 int futbol_rollout_slices(FutbolHandle *h, int K)
 {
     if (h == nullptr || K <= 0) return fail(FUTBOL_ERR_ARG, "null handle or K <= 0%s");
-    return h->is_v1 ? 1 : v0_rollout_slices(h->v0, K, h->rollout_slices);
+    return h->is_v1 ? 1 : v0_plan_rollout(h->v0, K, h->rollout_slices, h->rollout_variant).slices;
+}
+
+int futbol_rollout_kernel(FutbolHandle *h, int K)
+{
+    if (h == nullptr || K <= 0) return fail(FUTBOL_ERR_ARG, "null handle or K <= 0%s");
+    if (h->is_v1) return 0;
+    const V0RolloutChoice c = v0_plan_rollout(h->v0, K, h->rollout_slices, h->rollout_variant);
+    return c.kernel == 1 ? 2 : (c.slices > 1 ? 1 : 0);
+}
+
+int futbol_set_rollout_variant(FutbolHandle *h, int variant)
+{
+    if (h == nullptr || variant < 0 || variant > 2) return fail(FUTBOL_ERR_ARG, "null handle or variant not in 0..2%s");
+    h->rollout_variant = variant;
+    return FUTBOL_OK;
 }
 
 int futbol_set_rollout_slices(FutbolHandle *h, int slices)
@@ -239,7 +256,7 @@ int futbol_rollout_vs(FutbolHandle *h, void *state, int K, const uint8_t *action
     if (!h->initialised) return fail(FUTBOL_ERR_ARG, "futbol_reset must be called before futbol_rollout%s");
     if (h->is_v1 && ((uintptr_t)actions & 1u)) return fail(FUTBOL_ERR_ARG, "v1: the action buffer must be 2-byte aligned%s");
     cudaError_t e = h->is_v1 ? v1::launch_rollout(h->v1, state, K, actions, opp_actions, obs, reward, done, stats, (cudaStream_t)stream)
-                             : v0_launch_rollout(h->v0, state, K, actions, opp_actions, obs, reward, done, stats, h->rollout_slices, (cudaStream_t)stream);
+                             : v0_launch_rollout(h->v0, state, K, actions, opp_actions, obs, reward, done, stats, h->rollout_slices, h->rollout_variant, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     h->launches += 1;
     return FUTBOL_OK;

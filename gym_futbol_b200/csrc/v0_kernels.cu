@@ -141,6 +141,46 @@ __device__ __forceinline__ void warp_store_obs_f32(Lane L, const V0Regs &s, floa
     __syncwarp();
 }
 
+// The same tile in THREE passes of ten values per environment through the 1536-byte area of the draw words (dense
+// rollout kernels: 7936 B of shared memory per warp = seven blocks = 28 warps per SM, which holds a 131,072-env rank
+// batch -- 4096 warps on 148 x 28 = 4144 slots -- in ONE wave).  A pass stages [32 envs][10 floats] = 160 float2; float2 u of
+// the area belongs to env u / 5 and goes to float2 15 (u / 5) + 5 pass + u % 5 of the warp's tile: 40-byte runs, 8-byte stores.
+__device__ __forceinline__ void warp_store_obs_f32_3pass(Lane L, const V0Regs &s, float *stage, float *gdst_warp_row0,
+                                                         int lane, int rows_in_warp, bool vec_ok)
+{
+    float2 *mine = reinterpret_cast<float2 *>(stage) + lane * 5;
+#pragma unroll 1
+    for (int p = 0; p < 3; ++p) {
+        __syncwarp();                                  // pass 0: the draws are dead; later: the previous pass has been read
+        if (p < 2) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) mine[c] = make_float2((float)L.f((10 * p + 2 * c) * kLanes), (float)L.f((10 * p + 2 * c + 1) * kLanes));
+        } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) mine[c] = make_float2((float)L.f((20 + 2 * c) * kLanes), (float)L.f((21 + 2 * c) * kLanes));
+            mine[2] = make_float2((float)L.f(24 * kLanes), (float)obs_owner_elem(s, 0));
+            mine[3] = make_float2((float)obs_owner_elem(s, 1), (float)obs_owner_elem(s, 2));
+            mine[4] = make_float2((float)obs_owner_elem(s, 3), (float)obs_owner_elem(s, 4));
+        }
+        __syncwarp();
+        const float2 *src = reinterpret_cast<const float2 *>(stage);
+        if (vec_ok) {
+            float2 *dst = reinterpret_cast<float2 *>(gdst_warp_row0);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int u = lane + 32 * i, e = (u * 205) >> 10;            // u / 5 for u < 160
+                if (e < rows_in_warp) __stcs(dst + 15 * e + 5 * p + (u - 5 * e), src[u]);
+            }
+        } else {
+            for (int q = lane; q < 320; q += 32) {
+                const int e = q / 10;
+                if (e < rows_in_warp) __stcs(gdst_warp_row0 + 30 * e + 10 * p + (q - 10 * e), stage[q]);
+            }
+        }
+    }
+    __syncwarp();
+}
+
 template <typename T>
 __device__ __forceinline__ void thread_store_obs(T *dst_row, Lane L, const V0Regs &s)
 {
@@ -215,7 +255,7 @@ __global__ void __launch_bounds__(kEnvThreads, FUTBOL_MIN_BLOCKS) v0_step_kernel
 
 // Steps [k0, k1) of the rollout for the 128 envs of block-group `group`: state HBM -> shared memory, the steps,
 // state back.  One call per block in the plain rollout; one call per work unit in the time-sliced one.
-template <bool RANDOM_OPP>
+template <bool RANDOM_OPP, bool DENSE = false>
 __device__ __forceinline__ void rollout_span(const V0Params &P, const StateView &v, int group, int k0, int k1,
                                              const uint8_t *__restrict__ actions, const uint8_t *__restrict__ opp_actions,
                                              float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done,
@@ -229,11 +269,12 @@ __device__ __forceinline__ void rollout_span(const V0Params &P, const StateView 
     const int rows_in_warp = min(32, P.n_envs - warp_env0);
     const size_t n = (size_t)P.n_envs;
     // 128-bit stores need every step's row block 16-byte aligned: n*30*4 % 16 == 0  <=>  n even
-    const bool vec_ok = ((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
+    const bool vec_ok = ((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);   // (8-byte stores: always true then)
     const uint32_t env_id = P.env_id_offset + (uint32_t)i;
-    const Lane L = make_lane(warp, lane);
-    float *stage = reinterpret_cast<float *>(futbol_smem + warp * kWarpSmemBytes + kWarpStateBytes);
-    constexpr bool kBulk = FUTBOL_BULK_STORE && RANDOM_OPP;
+    constexpr int kWB = DENSE ? kWarpSmemBytesDense : kWarpSmemBytes;
+    const Lane L = make_lane(warp, lane, kWB);
+    float *stage = reinterpret_cast<float *>(futbol_smem + warp * kWB + kWarpStateBytes);
+    constexpr bool kBulk = FUTBOL_BULK_STORE && RANDOM_OPP && !DENSE;
 
     V0Regs s;
     if (live) load_state(v, i, L, s);
@@ -269,8 +310,11 @@ __device__ __forceinline__ void rollout_span(const V0Params &P, const StateView 
         fixes += (r.flags & kFlagFix) != 0;
         episodes += r.done;
         if (r.done && P.auto_reset) reset_env(L, s);
-        if (obs != nullptr)
-            warp_store_obs_f32<kBulk>(L, s, stage, obs + ((size_t)k * n + (size_t)warp_env0) * kObsDim, lane, rows_in_warp, vec_ok);
+        if (obs != nullptr) {
+            float *tile = obs + ((size_t)k * n + (size_t)warp_env0) * kObsDim;
+            if (DENSE) warp_store_obs_f32_3pass(L, s, stage, tile, lane, rows_in_warp, (reinterpret_cast<uintptr_t>(tile) & 7) == 0);
+            else warp_store_obs_f32<kBulk>(L, s, stage, tile, lane, rows_in_warp, vec_ok);
+        }
         if (live) {
             if (reward != nullptr) __stcs(reward + slot, (float)r.reward);
             if (done != nullptr) done[slot] = (uint8_t)r.done;
@@ -307,6 +351,18 @@ v0_rollout_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ ac
                   float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
 {
     rollout_span<RANDOM_OPP>(P, v, blockIdx.x, 0, K, actions, opp_actions, obs, reward, done, stats);
+}
+
+// The dense variant: 7936 B of shared memory per warp and 72 registers -> seven blocks = 28 warps per SM (4144 warp slots on a
+// B200): the rank-sized batches of the 2^20 job (131,072 / 262,144 / 524,288 envs = 4096 / 8192 / 16384 warps) are then one, two
+// and four nearly full waves, where 20 warps per SM leave 1.38 / 2.77 / 5.5.
+constexpr int kEnvSmemBytesDense = (kEnvThreads / 32) * kWarpSmemBytesDense;
+template <bool RANDOM_OPP>
+__global__ void __launch_bounds__(kEnvThreads, 7)
+v0_rollout_dense_kernel(V0Params P, StateView v, int K, const uint8_t *__restrict__ actions, const uint8_t *__restrict__ opp_actions,
+                        float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
+{
+    rollout_span<RANDOM_OPP, true>(P, v, blockIdx.x, 0, K, actions, opp_actions, obs, reward, done, stats);
 }
 
 // Time-sliced rollout for batches of only a few waves of blocks (131,072 envs per GPU = 1024 blocks on 740 block slots:
@@ -423,54 +479,67 @@ static int rollout_block_slots()
     return s;
 }
 
-// Number of time slices a K-step rollout of this batch is cut into (1 = the plain kernel).
-// Plain launch when the batch is under one wave (nothing to balance) or many waves (the tail is a few percent).
-// In between, slice the K steps so that the queue holds five to six waves of units: each unit pays one state round
-// trip, and measured on a B200 (tools/time_rank_batch.py, K = 64) 4 slices are best for 131,072 envs (+18 % over
-// the plain launch), 2 for 262,144 (+3 %); finer slicing loses more to the round trips than the shorter tail gains.
-int v0_rollout_slices(const V0Params &P, int K, int slices)
+// How a K-step rollout of this batch is launched (profiles/r2_slices.md has the measurements behind the rule).
+//   slices: 0 = automatic: the time-sliced work-queue launch (four slices at K = 64) when the batch is between one and two
+//   waves of blocks -- 131,072 envs, one of eight ranks of the 2^20 job: +8 % over the plain launch -- and the plain
+//   launch otherwise: from about 2.8 waves on the plain launch wins (262,144 envs: 1.677 vs 1.738 ms), because blocks of a
+//   thinning last wave run faster than blocks of a full one, while every slice pays the hand-over.  1 = never slice,
+//   n > 1 = n equal slices (futbol_set_rollout_slices: tests, tuning).
+//   variant: 0 / 1 = the standard kernel, 2 = the dense kernel (28 warps per SM).  Never chosen automatically: its
+//   three-pass observation staging and 72-register budget cost more than its whole waves gain (2^20 envs: 6.91 vs 6.37 ms;
+//   131,072: 0.942 vs 0.889 ms sliced); kept selectable so that the measurement can be repeated.
+V0RolloutChoice v0_plan_rollout(const V0Params &P, int K, int slices, int variant)
 {
+    V0RolloutChoice c;
+    c.kernel = variant == 2 ? 1 : 0;
+    c.slices = 1;
+    if (c.kernel == 1) return c;
     const int groups = blocks_for(P.n_envs, kEnvThreads);
     const int slots = P.random_opp ? rollout_block_slots<true>() : rollout_block_slots<false>();
-    int chunks = 1;
-    if (slices > 0) chunks = slices < K ? slices : K;               // futbol_set_rollout_slices: tests, tuning
-    else if (groups > slots && groups < 6 * slots) {
-        chunks = (11 * slots + 2 * groups - 1) / (2 * groups);
-        if (chunks > K / 4) chunks = K / 4;
+    int n = 1;
+    if (slices > 0) n = slices < K ? slices : K;
+    else if (groups > slots && groups < 2 * slots) {
+        n = (11 * slots + 2 * groups - 1) / (2 * groups);          // five to six waves of units
+        if (n > K / 4) n = K / 4;
     }
-    if (chunks < 1) chunks = 1;
-    if (chunks == 1) return 1;
-    const int chunk_steps = (K + chunks - 1) / chunks;
-    return (K + chunk_steps - 1) / chunk_steps;
+    if (n > 1) {
+        const int chunk_steps = (K + n - 1) / n;
+        c.slices = (K + chunk_steps - 1) / chunk_steps;
+    }
+    return c;
 }
 
 template <bool RANDOM_OPP>
 static cudaError_t launch_rollout(const V0Params &P, const StateView &v, int K, const uint8_t *actions, const uint8_t *opp_actions,
-                                  float *obs, float *reward, uint8_t *done, FutbolStats *stats, int slices, cudaStream_t st)
+                                  float *obs, float *reward, uint8_t *done, FutbolStats *stats, int slices, int variant, cudaStream_t st)
 {
     const int groups = blocks_for(P.n_envs, kEnvThreads);
-    const int slots = rollout_block_slots<RANDOM_OPP>();
-    const int chunks = v0_rollout_slices(P, K, slices);
-    if (chunks == 1) {
+    const V0RolloutChoice c = v0_plan_rollout(P, K, slices, variant);
+    if (c.kernel == 1) {
+        v0_rollout_dense_kernel<RANDOM_OPP><<<groups, kEnvThreads, kEnvSmemBytesDense, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+        return cudaGetLastError();
+    }
+    if (c.slices == 1) {
         v0_rollout_kernel<RANDOM_OPP><<<groups, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
         return cudaGetLastError();
     }
-    const int chunk_steps = (K + chunks - 1) / chunks;
+    const int slots = rollout_block_slots<RANDOM_OPP>();
+    const int chunk_steps = (K + c.slices - 1) / c.slices;
     cudaError_t e = cudaMemsetAsync(v.sched, 0, v0_sched_words(v.np) * 4, st);
     if (e != cudaSuccess) return e;
-    const long long units = (long long)chunks * groups;
+    const long long units = (long long)c.slices * groups;
     const int grid = (int)(units < slots ? units : slots);
-    v0_rollout_sliced_kernel<RANDOM_OPP><<<grid, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, chunk_steps, chunks, groups, actions,
+    v0_rollout_sliced_kernel<RANDOM_OPP><<<grid, kEnvThreads, kEnvSmemBytes, st>>>(P, v, K, chunk_steps, c.slices, groups, actions,
                                                                                  opp_actions, obs, reward, done, stats);
     return cudaGetLastError();
 }
 
 cudaError_t v0_launch_rollout(const V0Params &P, void *state, int K, const uint8_t *actions, const uint8_t *opp_actions,
-                              float *obs, float *reward, uint8_t *done, FutbolStats *stats, int slices, cudaStream_t st)
+                              float *obs, float *reward, uint8_t *done, FutbolStats *stats, int slices, int variant, cudaStream_t st)
 {
     const StateView v = make_view(state, P.n_envs);
-    return P.random_opp ? launch_rollout<true>(P, v, K, actions, opp_actions, obs, reward, done, stats, slices, st)
-                        : launch_rollout<false>(P, v, K, actions, opp_actions, obs, reward, done, stats, slices, st);
+    return P.random_opp ? launch_rollout<true>(P, v, K, actions, opp_actions, obs, reward, done, stats, slices, variant, st)
+                        : launch_rollout<false>(P, v, K, actions, opp_actions, obs, reward, done, stats, slices, variant, st);
 }
 
 cudaError_t v0_launch_get_state(int n, const void *state, void *aos, cudaStream_t st)

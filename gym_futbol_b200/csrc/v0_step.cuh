@@ -83,6 +83,7 @@ constexpr int kWarpStateBytes = kStateWords * kLanes * 8;
 constexpr int kStepScratchBytes = kDrawWords * kLanes * 4;
 constexpr int kWarpScratchBytes = (kLanes * kObsDim * 4 > kStepScratchBytes) ? kLanes * kObsDim * 4 : kStepScratchBytes;
 constexpr int kWarpSmemBytes = kWarpStateBytes + kWarpScratchBytes;
+constexpr int kWarpSmemBytesDense = kWarpStateBytes + kStepScratchBytes;   // 7936 B: seven 128-thread blocks per SM
 constexpr int kX = 0, kY = kLanes, kTX = 2 * kLanes, kTY = 3 * kLanes, kSP = 4 * kLanes;   // field offsets in a row
 constexpr int kRowStride = 5 * kLanes;
 constexpr int kBallRow = 4;
@@ -102,11 +103,13 @@ struct Lane {
     __device__ __forceinline__ uint32_t &draw(uint32_t j) const { return reinterpret_cast<uint32_t *>(futbol_smem)[dw + j * kLanes]; }
 };
 
-__device__ __forceinline__ Lane make_lane(int warp_in_block, int lane)
+// warp_bytes: shared memory per warp of the calling kernel (kWarpSmemBytes, or kWarpSmemBytesDense for the rollout
+// kernels that stage the observation in three passes through the draw words' area)
+__device__ __forceinline__ Lane make_lane(int warp_in_block, int lane, int warp_bytes = kWarpSmemBytes)
 {
     Lane L;
-    L.st = (uint32_t)(warp_in_block * (kWarpSmemBytes / 8) + lane);
-    L.dw = (uint32_t)(warp_in_block * (kWarpSmemBytes / 4) + kWarpStateBytes / 4 + lane);
+    L.st = (uint32_t)(warp_in_block * (warp_bytes / 8) + lane);
+    L.dw = (uint32_t)(warp_in_block * (warp_bytes / 4) + kWarpStateBytes / 4 + lane);
     return L;
 }
 

@@ -97,6 +97,18 @@ class FutbolVecEnv:
         """Number of time slices ``rollout(K)`` will use on this device (1 = the plain kernel)."""
         return int(self.lib.futbol_rollout_slices(self._h, int(K)))
 
+    ROLLOUT_KERNELS = ("v0_rollout_kernel", "v0_rollout_sliced_kernel", "v0_rollout_dense_kernel")
+
+    def rollout_kernel(self, K):
+        """Name of the kernel ``rollout(K)`` launches on this device (v1: always its one rollout kernel)."""
+        if self.act_shape:
+            return "v1_rollout_kernel"
+        return self.ROLLOUT_KERNELS[int(self.lib.futbol_rollout_kernel(self._h, int(K)))]
+
+    def set_rollout_variant(self, variant):
+        """0 = automatic, 1 = always the standard kernel (20 warps per SM), 2 = always the dense one (28).  Results are identical."""
+        _lib.check(self.lib.futbol_set_rollout_variant(self._h, int(variant)))
+
     def set_rollout_slices(self, slices):
         """Time slicing of ``rollout`` (include/futbol_b200.h): 0 = automatic, 1 = off, n = n slices.  Results are identical."""
         _lib.check(self.lib.futbol_set_rollout_slices(self._h, int(slices)))

@@ -180,11 +180,17 @@ uint64_t futbol_launch_count(const FutbolHandle *h);
  * futbol_rollout on a batch of only a few waves of thread blocks (e.g. 131,072 envs: one of eight ranks of the 2^20 job)
  * cuts the K steps into time slices and lets a grid that just fills the GPU take (slice, env-block) units from a queue,
  * so that no SM idles through a partial last wave.  Results do not depend on the slicing.  slices: 0 = chosen per
- * launch from the batch size (default), 1 = never slice, n > 1 = n slices.  v0 only; ignored for v1.  No reference
- * counterpart. */
+ * launch from the batch size (default: sliced between one and two waves of blocks), 1 = never slice, n > 1 = n equal
+ * slices.  v0 only; ignored for v1.  No reference counterpart. */
 int futbol_set_rollout_slices(FutbolHandle *h, int slices);
 /* the number of time slices futbol_rollout will use for K steps on the current device (1 = the plain kernel) */
 int futbol_rollout_slices(FutbolHandle *h, int K);
+/* which kernel futbol_rollout will launch for K steps on the current device: 0 = standard (20 warps per SM), 1 = standard,
+ * time-sliced, 2 = dense (28 warps per SM) */
+int futbol_rollout_kernel(FutbolHandle *h, int K);
+/* 0 / 1 = the standard kernel (default), 2 = the dense kernel: 7936 B of shared memory per warp and 72 registers, so that a
+ * batch of a few waves fills whole waves; measured slower, kept selectable.  Results do not depend on it. */
+int futbol_set_rollout_variant(FutbolHandle *h, int variant);
 
 #ifdef __cplusplus
 }

@@ -105,3 +105,43 @@ def test_sliced_rollout_is_cuda_graph_capturable():
         ob, rb, db = b.rollout(K, actions=acts)
         torch.cuda.synchronize()
         assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+
+
+
+@pytest.mark.parametrize("random_opp", [False, True])
+@pytest.mark.parametrize("n,K", [(4096 + 77, 64), (31, 20), (131072, 16)])
+def test_dense_kernel_equals_standard(n, K, random_opp):
+    """The dense rollout kernel (28 warps per SM, observation staged in three passes) gives the bytes of the standard one."""
+    import torch
+    from gym_futbol_b200 import FutbolVecEnv
+    runs = []
+    for variant in (1, 2):
+        env = FutbolVecEnv(n, seed=11, env_id_offset=4242, random_opp=random_opp, game_time=3.0)
+        env.set_rollout_variant(variant)
+        assert env.rollout_kernel(K) == ("v0_rollout_kernel", "v0_rollout_dense_kernel")[variant - 1]
+        env.reset()
+        outs = []
+        for rep in range(2):
+            o, r, d = env.rollout(K)
+            outs += [o.clone(), r.clone(), d.clone()]
+        torch.cuda.synchronize()
+        runs.append((outs, env.get_state().tobytes(), env.read_stats()))
+    for a, b in zip(runs[0][0], runs[1][0]):
+        assert torch.equal(a.view(torch.uint8), b.view(torch.uint8))
+    assert runs[0][1] == runs[1][1]
+    for key in ("env_steps", "episodes", "goals_ai", "goals_opp", "out_of_field"):
+        assert runs[0][2][key] == runs[1][2][key]
+
+
+def test_automatic_kernel_choice():
+    """Sliced between one and two waves of blocks (one rank of eight of the 2^20 job), plain otherwise; the dense kernel only
+    on request."""
+    from gym_futbol_b200 import FutbolVecEnv
+    assert FutbolVecEnv(4096, seed=0).rollout_kernel(64) == "v0_rollout_kernel"          # under one wave
+    env = FutbolVecEnv(131072, seed=0)
+    assert env.rollout_kernel(64) == "v0_rollout_sliced_kernel" and env.rollout_slices(64) == 4
+    env.set_rollout_slices(1)
+    assert env.rollout_kernel(64) == "v0_rollout_kernel"
+    env.set_rollout_variant(2)
+    assert env.rollout_kernel(64) == "v0_rollout_dense_kernel"
+    assert FutbolVecEnv(262144, seed=0).rollout_kernel(64) == "v0_rollout_kernel"        # 2.8 waves: plain wins

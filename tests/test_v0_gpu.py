@@ -130,7 +130,7 @@ def test_golden_reference_traces(torch_cuda, golden_v0):
         env.close()
         checked += 1
         steps += m["steps"]
-    assert checked >= 42 and steps >= 13000
+    assert checked >= 42 and steps >= 11000
 
 
 def test_wide_reference_set_split_rate(torch_cuda):
