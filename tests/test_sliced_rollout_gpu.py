@@ -118,6 +118,7 @@ def test_dense_kernel_equals_standard(n, K, random_opp):
     for variant in (1, 2):
         env = FutbolVecEnv(n, seed=11, env_id_offset=4242, random_opp=random_opp, game_time=3.0)
         env.set_rollout_variant(variant)
+        env.set_rollout_slices(1)
         assert env.rollout_kernel(K) == ("v0_rollout_kernel", "v0_rollout_dense_kernel")[variant - 1]
         env.reset()
         outs = []
