@@ -344,7 +344,7 @@ def main():
     stats = torch.from_numpy(env.stats.cpu().numpy().view("int64").copy()).to(dev)   # optional statistics gather
     if world > 1:
         dist.all_reduce(stats[1:6], op=dist.ReduceOp.SUM)
-    slices = env.rollout_slices(K)
+    slices, kernel_name = env.rollout_slices(K), env.rollout_kernel(K)
     h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
     del pipe, acts
     env.close()
@@ -397,8 +397,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(n_local, K), "peak_source": peak_src,
-                         "kernel": ("v0_rollout_sliced_kernel (the same step code; (time slice, env block) units from a work queue, "
-                                    "%d slices)" % slices) if slices > 1 else "v0_rollout_kernel",
+                         "kernel": ("%s (the same step code; (time slice, env block) units from a work queue, %d slices)"
+                                    % (kernel_name, slices)) if slices > 1 else kernel_name,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": n_local * K * BYTES_PER_ENV_STEP,
                          "note": "the kernel is instruction-issue bound (fp64 IEEE sqrt/div sequences, selects, Philox), "

@@ -69,17 +69,6 @@ __device__ __forceinline__ void philox_fill_block(uint32_t *col, const PhiloxKey
     dst[0] = p.x; dst[kLanes] = p.y; dst[2 * kLanes] = p.z; dst[3 * kLanes] = p.w;
 }
 
-// the first two blocks, computed in registers first; `before_store()` runs between the arithmetic and the stores (the
-// rollout kernel waits there for the copy engine to release the area the words are parked in)
-template <typename F>
-__device__ __forceinline__ void philox_fill_two(uint32_t *col, const PhiloxKey &K, uint32_t env_id, uint32_t stream, uint64_t t, F before_store)
-{
-    const Philox4 p0 = philox_step_block(K, env_id, stream, t, 0u), p1 = philox_step_block(K, env_id, stream, t, 1u);
-    before_store();
-    col[0] = p0.x; col[kLanes] = p0.y; col[2 * kLanes] = p0.z; col[3 * kLanes] = p0.w;
-    col[4 * kLanes] = p1.x; col[5 * kLanes] = p1.y; col[6 * kLanes] = p1.z; col[7 * kLanes] = p1.w;
-}
-
 // blocks [0, n_blocks) of the step's sequential draws
 __device__ __forceinline__ void philox_fill_step(uint32_t *col, const PhiloxKey &K, uint32_t env_id, uint32_t stream, uint64_t t,
                                                  int n_blocks = kSeqBlocks)

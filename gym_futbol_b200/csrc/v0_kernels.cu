@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kEnvThreads, FUTBOL_MIN_BLOCKS) v0_step_kernel
 
 // Steps [k0, k1) of the rollout for the 128 envs of block-group `group`: state HBM -> shared memory, the steps,
 // state back.  One call per block in the plain rollout; one call per work unit in the time-sliced one.
-template <bool RANDOM_OPP, bool DENSE = false>
+template <bool RANDOM_OPP, bool DENSE = false, bool SLICED = false>
 __device__ __forceinline__ void rollout_span(const V0Params &P, const StateView &v, int group, int k0, int k1,
                                              const uint8_t *__restrict__ actions, const uint8_t *__restrict__ opp_actions,
                                              float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done,
@@ -295,14 +295,15 @@ __device__ __forceinline__ void rollout_span(const V0Params &P, const StateView 
         } else a = philox_action(P.key, env_id, s.t_total, 16);
         const int ai_before = s.ai_score;
         const int oa = (opp_actions != nullptr && live) ? (int)(__ldg(opp_actions + slot) & 15) : -1;
-        // the draw words are parked where the previous step's observation tile was staged: with the bulk store, wait (after
-        // the Philox arithmetic, in registers) until the copy engine has read that tile
+        // the draw words are parked where the previous step's observation tile was staged: with the bulk store, wait
+        // until the copy engine has read that tile
         const bool wait_tile = kBulk && obs != nullptr && k > k0;
-        const StepResult r = v0_step<RANDOM_OPP>(L, s, P, env_id, a, oa, [&]() {
+        auto before_draws = [&]() {
             if (kBulk) {
                 if (wait_tile) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
             }
-        });
+        };
+        const StepResult r = v0_step<RANDOM_OPP, decltype(before_draws), SLICED>(L, s, P, env_id, a, oa, before_draws);
         last_flags = r.flags;
         reward_sum += r.reward;
         goals_ai += (r.flags & kFlagGoal) && s.ai_score != ai_before;
@@ -394,8 +395,8 @@ v0_rollout_sliced_kernel(V0Params P, StateView v, int K, int chunk_steps, int ch
             }
         }
         __syncthreads();                       // also keeps unit_s from being overwritten while others still read it
-        rollout_span<RANDOM_OPP>(P, v, g, c * chunk_steps, min(K, (c + 1) * chunk_steps), actions, opp_actions, obs, reward,
-                                 done, stats);
+        rollout_span<RANDOM_OPP, false, true>(P, v, g, c * chunk_steps, min(K, (c + 1) * chunk_steps), actions, opp_actions, obs,
+                                              reward, done, stats);
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) progress[g] = (uint32_t)(c + 1);

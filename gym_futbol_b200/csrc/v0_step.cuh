@@ -358,6 +358,10 @@ __device__ __forceinline__ void resolve_pass(Lane L, const PendingShot &shot)
     L.f(bo + kSP) = dadd(lo, dmul(dsub(hi, lo), u));                     // random.uniform
 }
 
+// the same, out of line: the time-sliced rollout kernel runs 1.3 % faster with the pass resolved through a call (and the
+// plain kernel 1.3 % slower): code layout in an instruction-fetch-bound loop, measured (profiles/r2_v0_history.md)
+static __device__ __noinline__ void resolve_pass_outlined(Lane L, const PendingShot &shot) { resolve_pass(L, shot); }
+
 // Easy_Agent.get_action_type for 'right' opponent `a`, easy_agent.py:53-98
 __device__ __forceinline__ int easy_action(Lane L, uint32_t &j, int a, bool has_ball, bool team_has_ball)
 {
@@ -429,14 +433,16 @@ struct StepResult { double reward; int done; int flags; };
 // for opp_1 (a / 4) and opp_2 (a % 4), the self-play hook: same path as the random opponents (:642-645), the
 // randint(0, 15) draw is not taken.
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
-template <bool RANDOM_OPP, typename Hook = NoHook>
+template <bool RANDOM_OPP, typename Hook = NoHook, bool OUTLINE_PASS = false>
 __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params &P, uint32_t env_id, int ai_action, int opp_action = -1,
                                               Hook before_draw_store = Hook())
 {
-    // Two Philox blocks = the first eight sequential draws up front; the third block (draws 9 and 10) only when the last
-    // turn is about to consume one of them: never with the hard-coded opponents in 5,400 reference steps, 1.2 % of the
-    // steps with random ones (draw counts of tests/golden/v0_golden.npz), against 52 instructions on every step.
-    philox_fill_two(&L.draw(0), P.key, env_id, kStreamDynamics, s.t_total, before_draw_store);
+    // All three Philox blocks (twelve words) up front.  Generating the third one -- draws 9 and 10: never consumed with the
+    // hard-coded opponents in 5,400 reference steps, in 1.2 % of the steps with random ones -- only on demand saves 39
+    // instructions per warp-step and was measured SLOWER (2^20 envs: 1.052e10 against 1.078e10 env-steps/s): the test before
+    // the last turn and the second copy of the block cost the instruction-fetch-bound loop more (profiles/r2_v0_history.md).
+    before_draw_store();
+    philox_fill_step(&L.draw(0), P.key, env_id, kStreamDynamics, s.t_total);
     uint32_t j = 0;
     PendingShot shot;
     shot.shooter = -1; shot.target_y = 0; shot.pick_idx = 0; shot.passer = -1; shot.pass_w = 0;
@@ -498,13 +504,7 @@ __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params 
         const bool has_ball = latched ? (t == 0 ? has1 : has2) : s.owner == a;
         const int action = t == 0 ? opp_a1 : (t == 1 ? opp_a2 : (t == 2 ? action1 : action2));
         const bool set_target = latched && (t == 0 ? set1 : set2);
-        // Draws 9 and 10 (words 8 and 9) can only be consumed by the LAST turn: before turn 2 at most 1 + 3 + 2 = 6 draws
-        // are gone, and only after a shot (no second one can follow), so turn 2 ends at word 7.  The last turn consumes
-        // word j, word j + 1 when it draws (has-ball run / shoot / assist, no-ball intercept) and word j + 2 when it shoots.
-        if (t == 3) {
-            if (j + ((has_ball != (action == kIntercept)) ? 1u : 0u) + ((has_ball && action == kShoot) ? 1u : 0u) >= 8u)
-                philox_fill_block(&L.draw(0), P.key, env_id, kStreamDynamics, s.t_total, 2);
-        }
+
         player_turn(L, j, s, P, a, has_ball, action, set_target, t == 0 ? t1x : t2x, t == 0 ? t1y : t2y, shot);
         if (!RANDOM_OPP && t == 1) {
             // :962-982 anticipate the ball: whoever can reach its next position lands exactly on it
@@ -528,6 +528,7 @@ __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params 
     }
     if ((shot.shooter & shot.passer) >= 0) {                             // at most one of the two is pending (both -1: skip)
         if (shot.shooter >= 0) resolve_shot(L, s, P, RANDOM_OPP, env_id, shot);
+        else if (OUTLINE_PASS) resolve_pass_outlined(L, shot);
         else resolve_pass(L, shot);
     }
 

@@ -34,6 +34,6 @@ torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 print("rank %d bind=%s cpus=%d: D2H %.1f GB/s" % (rank, bind, len(os.sched_getaffinity(0)), 8 * nbytes / dt / 1e9), flush=True)
 dist.barrier()
-if rank == 0 and not bind:
+if False and rank == 0 and not bind:
     print(subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True).stdout[:3000])
 dist.destroy_process_group()
