@@ -159,8 +159,11 @@ __global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, 
     }
 }
 
-template <int REGC>
-__global__ void v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t *__restrict__ actions,
+// MINB: resident 64-thread blocks per SM the register allocation is capped for.  Measured (tools/exp_variants_v1.sh, end of
+// round 2): the small teams, whose shared-memory state is small, gain from more warps -- 1v1 +3.9 % at 12 blocks (85
+// registers), 2v2 +1.8 % at 10 (102) -- from 3v3 on the uncapped allocation wins.
+template <int REGC, int MINB>
+__global__ void __launch_bounds__(64, MINB) v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t *__restrict__ actions,
                                   const uint8_t *__restrict__ opp_actions, float *__restrict__ obs,
                                   float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
 {
@@ -288,7 +291,7 @@ static inline int threads_for(int n_players) { return n_players <= 5 ? 64 : 32; 
 #ifdef FUTBOL_V1_REGC
 static inline int regc_for(int) { return FUTBOL_V1_REGC; }     // tuning builds (tools/build_variant.py)
 #else
-static inline int regc_for(int n_players) { return n_players >= 7 ? 3 : (n_players >= 4 ? 2 : (n_players >= 2 ? 1 : 0)); }
+static inline int regc_for(int n_players) { return n_players >= 7 ? 3 : (n_players >= 4 ? 2 : (n_players >= 3 ? 1 : 0)); }
 #endif   // contacts kept in registers by the solver (v1_step.cuh space_step)
 static inline int smem_for(int n_players) { return block_smem_bytes(n_players, threads_for(n_players) / 32); }
 
@@ -325,10 +328,11 @@ cudaError_t launch_rollout(const V1Params &P, void *state, int K, const uint8_t 
     const StateView v = make_view(state, P.n_envs, P.n_players);
     const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
     const int g = blocks_for(P.n_envs, t), rc = regc_for(P.n_players);
-    if (rc == 3) v1_rollout_kernel<3><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
-    else if (rc == 2) v1_rollout_kernel<2><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
-    else if (rc == 1) v1_rollout_kernel<1><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
-    else v1_rollout_kernel<0><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+    if (rc == 3) v1_rollout_kernel<3, 1><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+    else if (rc == 2) v1_rollout_kernel<2, 1><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+    else if (rc == 1) v1_rollout_kernel<1, 1><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+    else if (P.n_players == 1) v1_rollout_kernel<0, 12><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
+    else v1_rollout_kernel<0, 10><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
     return cudaGetLastError();
 }
 
