@@ -9,19 +9,22 @@ probe=$out/${tag}_d2h_probe.txt
 : > $probe
 nvidia-smi topo -m >> $probe 2>&1
 echo "host: $(nproc) CPUs, $(grep -c processor /proc/cpuinfo) logical, NUMA nodes: $(ls -d /sys/devices/system/node/node* 2>/dev/null | wc -l)" >> $probe
-for n in 1 2 4 8; do
+for n in ${PROBE_RANKS:-1 2 4 8}; do
   for mode in nobind bind; do
     echo "--- $n ranks, $mode" >> $probe
     run $n tools/d2h_probe.py $mode 2>/dev/null | grep -E "^rank" | sort >> $probe
   done
 done
-run 8 bench.py --gpus 8 --steps 10 --warmup 3 > $out/${tag}_bench_n8.json 2> $out/${tag}_bench_n8.err
+if [ -z "$SKIP_PROBE_BENCH" ]; then
 run 8 bench.py --gpus 8 --steps 10 --warmup 3 --bind-cpus 0 > $out/${tag}_bench_n8_nobind.json 2> $out/${tag}_bench_n8_nobind.err
-run 2 bench.py --gpus 2 --steps 10 --warmup 3 > $out/${tag}_bench_n2.json 2> $out/${tag}_bench_n2.err
-python bench.py --gpus 1 --steps 10 --warmup 3 --no-configs --no-cpu-baseline > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
+fi
+run 8 bench.py --gpus 8 --steps 20 --warmup 3 > $out/${tag}_bench_n8.json 2> $out/${tag}_bench_n8.err
+run 4 bench.py --gpus 4 --steps 20 --warmup 3 > $out/${tag}_bench_n4.json 2> $out/${tag}_bench_n4.err
+run 2 bench.py --gpus 2 --steps 20 --warmup 3 > $out/${tag}_bench_n2.json 2> $out/${tag}_bench_n2.err
+python bench.py --gpus 1 --steps 20 --warmup 3 --no-configs --no-cpu-baseline > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
 python - <<PY
 import json
-for n in ("n1", "n2", "n8", "n8_nobind"):
+for n in ("n1", "n2", "n4", "n8", "n8_nobind"):
     try:
         d = json.load(open("$out/${tag}_bench_%s.json" % n))
         print(n, "value %.3e kernel_ms %.3f e2e %.3e resident %.3e d2h %.1f of %.1f GB/s per GPU" % (
