@@ -303,7 +303,13 @@ __device__ __forceinline__ void rollout_span(const V0Params &P, const StateView 
                 if (wait_tile) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
             }
         };
-        const StepResult r = v0_step<RANDOM_OPP, decltype(before_draws), SLICED>(L, s, P, env_id, a, oa, before_draws);
+#ifndef FUTBOL_SLICED_LAYOUT
+#define FUTBOL_SLICED_LAYOUT 1
+#endif
+#ifndef FUTBOL_PLAIN_LAYOUT
+#define FUTBOL_PLAIN_LAYOUT 0
+#endif
+        const StepResult r = v0_step<RANDOM_OPP, decltype(before_draws), SLICED ? FUTBOL_SLICED_LAYOUT : FUTBOL_PLAIN_LAYOUT>(L, s, P, env_id, a, oa, before_draws);
         last_flags = r.flags;
         reward_sum += r.reward;
         goals_ai += (r.flags & kFlagGoal) && s.ai_score != ai_before;

@@ -361,6 +361,8 @@ __device__ __forceinline__ void resolve_pass(Lane L, const PendingShot &shot)
 // the same, out of line: the time-sliced rollout kernel runs 1.3 % faster with the pass resolved through a call (and the
 // plain kernel 1.3 % slower): code layout in an instruction-fetch-bound loop, measured (profiles/r2_v0_history.md)
 static __device__ __noinline__ void resolve_pass_outlined(Lane L, const PendingShot &shot) { resolve_pass(L, shot); }
+static __device__ __noinline__ void resolve_shot_outlined(Lane L, const V0Regs &s, const V0Params &P, bool random_opp, uint32_t env_id,
+                                                          const PendingShot &shot) { resolve_shot(L, s, P, random_opp, env_id, shot); }
 
 // Easy_Agent.get_action_type for 'right' opponent `a`, easy_agent.py:53-98
 __device__ __forceinline__ int easy_action(Lane L, uint32_t &j, int a, bool has_ball, bool team_has_ball)
@@ -433,7 +435,9 @@ struct StepResult { double reward; int done; int flags; };
 // for opp_1 (a / 4) and opp_2 (a % 4), the self-play hook: same path as the random opponents (:642-645), the
 // randint(0, 15) draw is not taken.
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
-template <bool RANDOM_OPP, typename Hook = NoHook, bool OUTLINE_PASS = false>
+// LAYOUT (code layout of the rare / repeated parts; results are identical): bit 0 = the pending pass resolved through a call,
+// bit 1 = the pending shot resolved through a call, bit 2 = the five kinematics rows through one out-of-line copy
+template <bool RANDOM_OPP, typename Hook = NoHook, int LAYOUT = 0>
 __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params &P, uint32_t env_id, int ai_action, int opp_action = -1,
                                               Hook before_draw_store = Hook())
 {
@@ -527,13 +531,18 @@ __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params 
         }
     }
     if ((shot.shooter & shot.passer) >= 0) {                             // at most one of the two is pending (both -1: skip)
-        if (shot.shooter >= 0) resolve_shot(L, s, P, RANDOM_OPP, env_id, shot);
-        else if (OUTLINE_PASS) resolve_pass_outlined(L, shot);
+        if (shot.shooter >= 0) {
+            if (LAYOUT & 2) resolve_shot_outlined(L, s, P, RANDOM_OPP, env_id, shot);
+            else resolve_shot(L, s, P, RANDOM_OPP, env_id, shot);
+        } else if (LAYOUT & 1) resolve_pass_outlined(L, shot);
         else resolve_pass(L, shot);
     }
 
     // ---- kinematics, :661-663 ----
-    advance_all(L);
+    if (LAYOUT & 4) {
+#pragma unroll 1
+        for (int r = 0; r < 5; ++r) { const XY n = advance_row(L, r * kRowStride); L.f(r * kRowStride + kX) = n.x; L.f(r * kRowStride + kY) = n.y; }
+    } else advance_all(L);
 
     // ---- _get_reward, :752-861 (evaluated before the goal re-kickoff) ----
     const double ball_x = L.f(bo + kX), ball_y = L.f(bo + kY);
