@@ -106,10 +106,8 @@ __device__ __forceinline__ void warp_store_obs_f32(Lane L, int N, float *gdst_wa
 }
 
 template <typename T>
-__global__ void v1_reset_kernel(V1Params P, StateView v, const uint8_t *mask, T *obs, int init)
+__global__ void v1_reset_kernel(const __grid_constant__ V1Params P, StateView v, const uint8_t *mask, T *obs, int init)
 {
-    const uint32_t form_base = stage_formation(P, blockDim.x >> 5, threadIdx.x, blockDim.x);
-    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_envs) return;
     if (mask != nullptr && mask[i] == 0) return;
@@ -117,18 +115,16 @@ __global__ void v1_reset_kernel(V1Params P, StateView v, const uint8_t *mask, T 
     const Lane L = make_lane(threadIdx.x >> 5, threadIdx.x & 31, N);
     const uint32_t env_id = P.env_id_offset + (uint32_t)i;
     V1Regs s;
-    if (init) init_env(L, s, P, env_id, form_base);
-    else { load_state(v, i, L, s, B); reset_env(L, s, P, env_id, form_base); }
+    if (init) init_env(L, s, P, env_id);
+    else { load_state(v, i, L, s, B); reset_env(L, s, P, env_id); }
     store_state(v, i, L, s, B, 0);
     if (obs != nullptr) thread_store_obs(obs + (size_t)i * obs_dim(N), L, N);
 }
 
 template <typename T, int REGC>
-__global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, const uint8_t *opp_actions, T *obs, T *reward,
+__global__ void v1_step_kernel(const __grid_constant__ V1Params P, StateView v, const uint8_t *actions, const uint8_t *opp_actions, T *obs, T *reward,
                                uint8_t *done, T *final_obs)
 {
-    const uint32_t form_base = stage_formation(P, blockDim.x >> 5, threadIdx.x, blockDim.x);
-    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int warp_env0 = i - lane;
@@ -143,11 +139,11 @@ __global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, 
         const PairCache C{v.cache + i, v.np};
         Contact con[kMaxContacts];
         load_state(v, i, L, s, B);
-        const StepResult r = v1_step<REGC>(L, s, P, env_id, actions + (size_t)i * 2 * N, C, con, form_base,
+        const StepResult r = v1_step<REGC>(L, s, P, env_id, actions + (size_t)i * 2 * N, C, con,
                                            opp_actions != nullptr ? opp_actions + (size_t)i * 2 * N : nullptr);
         if (r.done && P.auto_reset) {
             if (final_obs != nullptr) thread_store_obs(final_obs + (size_t)i * D, L, N);
-            reset_env(L, s, P, env_id, form_base);
+            reset_env(L, s, P, env_id);
         }
         store_state(v, i, L, s, B, r.flags);
         if (reward != nullptr) reward[i] = (T)r.reward;
@@ -163,12 +159,10 @@ __global__ void v1_step_kernel(V1Params P, StateView v, const uint8_t *actions, 
 // round 2): the small teams, whose shared-memory state is small, gain from more warps -- 1v1 +3.9 % at 12 blocks (85
 // registers), 2v2 +1.8 % at 10 (102) -- from 3v3 on the uncapped allocation wins.
 template <int REGC, int MINB>
-__global__ void __launch_bounds__(64, MINB) v1_rollout_kernel(V1Params P, StateView v, int K, const uint8_t *__restrict__ actions,
+__global__ void __launch_bounds__(64, MINB) v1_rollout_kernel(const __grid_constant__ V1Params P, StateView v, int K, const uint8_t *__restrict__ actions,
                                   const uint8_t *__restrict__ opp_actions, float *__restrict__ obs,
                                   float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
 {
-    const uint32_t form_base = stage_formation(P, blockDim.x >> 5, threadIdx.x, blockDim.x);
-    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warp_env0 = i - lane;
@@ -186,7 +180,7 @@ __global__ void __launch_bounds__(64, MINB) v1_rollout_kernel(V1Params P, StateV
 
     V1Regs s;
     if (live) load_state(v, i, L, s, B);
-    else init_env(L, s, P, env_id, form_base);
+    else init_env(L, s, P, env_id);
 
     double reward_sum = 0.0;
     uint32_t episodes = 0, goals_l = 0, goals_r = 0, outs = 0, contacts = 0, overflow = 0;
@@ -196,9 +190,9 @@ __global__ void __launch_bounds__(64, MINB) v1_rollout_kernel(V1Params P, StateV
         const size_t slot = (size_t)k * n + (size_t)i;
         StepResult r;
         if (live) {
-            r = v1_step<REGC>(L, s, P, env_id, actions != nullptr ? actions + slot * 2 * N : nullptr, C, con, form_base,
+            r = v1_step<REGC>(L, s, P, env_id, actions != nullptr ? actions + slot * 2 * N : nullptr, C, con,
                               opp_actions != nullptr ? opp_actions + slot * 2 * N : nullptr);
-            if (r.done && P.auto_reset) reset_env(L, s, P, env_id, form_base);
+            if (r.done && P.auto_reset) reset_env(L, s, P, env_id);
         } else {
             r.reward = 0.0; r.done = 0; r.flags = 0; r.contacts = 0; r.overflow = 0;
         }
@@ -286,7 +280,10 @@ static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 #ifdef FUTBOL_V1_THREADS
 static inline int threads_for(int) { return FUTBOL_V1_THREADS; }   // tuning builds (tools/build_variant.py)
 #else
-static inline int threads_for(int n_players) { return n_players <= 5 ? 64 : 32; }   // keeps a block under 48 KB of shared memory (10v10: 33 KB per warp)
+// The block size that lets the most warps be resident (228 KB of shared memory per SM, 1 KB reserved per block; a warp holds
+// 1536 (2N + 1) B of state): two warps per block up to 4v4 (16 warps at 4v4), one from 5v5 on (13 instead of 12 warps at 5v5,
+// 11 instead of 10 at 6v6, 7 at 10v10).
+static inline int threads_for(int n_players) { return n_players <= 4 ? 64 : 32; }
 #endif
 #ifdef FUTBOL_V1_REGC
 static inline int regc_for(int) { return FUTBOL_V1_REGC; }     // tuning builds (tools/build_variant.py)

@@ -78,16 +78,18 @@ struct V1Params {
 
 // ---- per-environment working storage --------------------------------------------------------------------
 // shared memory, one column per lane: element (6 * body + field) of lane l at st[(6 * body + field) * kCol + l],
-// kCol = 33: a lane walking its own column is conflict-free (consecutive lanes, consecutive words), and so is a
-// warp reading ONE lane's column element by element (the transposed read of the observation writer: consecutive
-// elements are 33 doubles apart = 2 banks, not 0);
+// kCol = 32: a lane walking its own column is conflict-free (consecutive lanes, consecutive words).  (Round 1 padded the
+// columns to 33 for an observation writer that read ONE lane's column element by element; the present writer reads four
+// fields of eight environments per instruction, for which 32 and 33 conflict alike, and without the padding -- and with
+// the kick-off formation read from the launch parameters instead of a shared-memory copy -- a 10v10 warp's state is
+// 32,256 B: SEVEN resident warps per SM instead of six.)
 // fields x, y, vx, vy, v_bias_x, v_bias_y; bodies: team A 0..N-1, team B N..2N-1, ball 2N.
 #ifndef FUTBOL_HOST_SHIM
 extern __shared__ __align__(16) unsigned char futbol_smem[];
 #else
-static unsigned char futbol_smem[8 * 6 * kMaxBodies + 16 + 8 * 4 * kMaxN] __attribute__((aligned(16)));
+static unsigned char futbol_smem[8 * 6 * kMaxBodies + 16] __attribute__((aligned(16)));
 #endif
-constexpr int kCol = kLanes == 1 ? 1 : kLanes + 1;
+constexpr int kCol = kLanes;
 constexpr int kPX = 0, kPY = kCol, kVX = 2 * kCol, kVY = 3 * kCol, kBX = 4 * kCol, kBY = 5 * kCol;
 constexpr int kBodyStride = 6 * kCol;
 
@@ -99,7 +101,7 @@ struct Lane {
 __host__ __device__ constexpr int warp_state_bytes(int n_players) { return ((6 * (2 * n_players + 1) * kCol * 8) + 15) & ~15; }
 __host__ __device__ constexpr int obs_dim(int n_players) { return 4 + 8 * n_players; }
 __host__ __device__ constexpr int warp_smem_bytes(int n_players) { return warp_state_bytes(n_players); }
-__host__ __device__ constexpr int block_smem_bytes(int n_players, int warps) { return warps * warp_smem_bytes(n_players) + 4 * n_players * 8; }
+__host__ __device__ constexpr int block_smem_bytes(int n_players, int warps) { return warps * warp_smem_bytes(n_players); }
 __host__ __device__ constexpr int n_pairs(int bodies) { return bodies * (bodies - 1) / 2 + bodies * kNSeg; }
 
 __device__ __forceinline__ Lane make_lane(int warp_in_block, int lane, int n_players)
@@ -193,46 +195,36 @@ __device__ __forceinline__ uint32_t draw(const V1Params &P, uint32_t env_id, uin
 // _position_to_initial, :129-143: teleport to the formation, zero velocities, space.step(1e-4).  With all
 // velocities zero the 1e-4 step only consumes the bias velocities (p += v_bias * 1e-4, v_bias = 0), finds no
 // contact (formation spacing >= 13.6) and ages the cached arbiters by one step.  Out of line (three call sites);
-// the formation is read from the block's copy in shared memory (form_base: index in doubles, x then y).
-static __device__ __noinline__ void position_to_initial(Lane L, int N, uint32_t form_base)
+// the formation is read from the launch parameters (constant bank; the kernels declare them __grid_constant__).
+static __device__ __noinline__ void position_to_initial(Lane L, const V1Params &P)
 {
-    const int B = 2 * N + 1;
-    const double *form = reinterpret_cast<const double *>(futbol_smem) + form_base;
+    const int N = P.n_players, B = 2 * N + 1;
 #pragma unroll 1
     for (int i = 0; i < B; ++i) {
         const int o = i * kBodyStride;
-        const double x = i < 2 * N ? form[i] : dmul(kWidth, 0.5), y = i < 2 * N ? form[2 * N + i] : dmul(kHeight, 0.5);
+        const double x = i < 2 * N ? P.form_x[i] : dmul(kWidth, 0.5), y = i < 2 * N ? P.form_y[i] : dmul(kHeight, 0.5);
         L.f(o + kPX) = dadd(x, dmul(dadd(0.0, L.f(o + kBX)), 0.0001));
         L.f(o + kPY) = dadd(y, dmul(dadd(0.0, L.f(o + kBY)), 0.0001));
         L.f(o + kVX) = 0.0; L.f(o + kVY) = 0.0; L.f(o + kBX) = 0.0; L.f(o + kBY) = 0.0;
     }
 }
 
-// every kernel copies the formation of its launch parameters to the tail of the block's shared memory once
-__device__ __forceinline__ uint32_t stage_formation(const V1Params &P, int warps_in_block, int tid, int nthreads)
-{
-    const uint32_t base = (uint32_t)(warps_in_block * (warp_smem_bytes(P.n_players) / 8));
-    double *form = reinterpret_cast<double *>(futbol_smem) + base;
-    for (int i = tid; i < 2 * P.n_players; i += nthreads) { form[i] = P.form_x[i]; form[2 * P.n_players + i] = P.form_y[i]; }
-    return base;
-}
-
-__device__ __forceinline__ void reset_env(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id, uint32_t form_base)
+__device__ __forceinline__ void reset_env(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id)
 {   // Futbol.reset, :145-150 (t_total, the Philox step index, is deliberately kept; so is the arbiter cache)
     s.ep_step = 0;
     s.owner_side = (int)__umulhi(philox_word_cold(P.seed, env_id, kStreamV1Dynamics, s.t_total, kResetBlock, 0u), 2u);
-    position_to_initial(L, P.n_players, form_base);
+    position_to_initial(L, P);
     s.stamp += 1;
 }
 
 // first construction (Futbol.__init__ -> reset): zero bias velocities, fresh stamps
-__device__ __forceinline__ void init_env(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id, uint32_t form_base)
+__device__ __forceinline__ void init_env(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id)
 {
     const int B = 2 * P.n_players + 1;
     for (int i = 0; i < B; ++i) { L.f(i * kBodyStride + kBX) = 0.0; L.f(i * kBodyStride + kBY) = 0.0; }
     s.t_total = 0;
     s.stamp = kStamp0;
-    reset_env(L, s, P, env_id, form_base);
+    reset_env(L, s, P, env_id);
 }
 
 // observation element k of the normalised vector [ball, team A, team B], :154-180
@@ -583,7 +575,7 @@ struct StepResult { double reward; int done; int flags; int contacts; int overfl
 // self-play hook) or nullptr = action_space.sample() (:429, Philox stream 2).
 template <int REGC>
 __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params &P, uint32_t env_id, const uint8_t *left,
-                                              const PairCache &C, Contact *con, uint32_t form_base, const uint8_t *right = nullptr)
+                                              const PairCache &C, Contact *con, const uint8_t *right = nullptr)
 {
     const int N = P.n_players, ball = 2 * N, bo = ball * kBodyStride;
     StepResult res;
@@ -681,7 +673,7 @@ __device__ __forceinline__ StepResult v1_step(Lane L, V1Regs &s, const V1Params 
     if (goal) {                                                          // :469-475
         const bool left_scored = L.f(bo + kPX) > kWidth - 2;
         reward = dadd(reward, left_scored ? 1000.0 : -1000.0);
-        position_to_initial(L, N, form_base);
+        position_to_initial(L, P);
         s.stamp += 1;
         s.owner_side = (int)__umulhi(draw(P, env_id, s.t_total, j), 2u);
         res.flags |= kFlagGoal | (left_scored ? (int)kFlagGoalLeft : 0);

@@ -46,7 +46,6 @@ void host_v1_rollout(uint64_t seed, uint32_t env_id0, int n_players, int ep_limi
     for (int i = 0; i < 2 * n_players; ++i) { P.form_x[i] = form_x[i]; P.form_y[i] = form_y[i]; }
     const int N = n_players, B = 2 * N + 1, D = 4 + 8 * N, NP = n_pairs(B);
     const Lane L = make_lane(0, 0, N);
-    const uint32_t form_base = stage_formation(P, 1, 0, 1);
     std::vector<CacheRec> cache(NP);
     Contact con[kMaxContacts];
     for (int i = 0; i < n; ++i) {
@@ -54,14 +53,14 @@ void host_v1_rollout(uint64_t seed, uint32_t env_id0, int n_players, int ep_limi
         PairCache C{cache.data(), 1};
         V1Regs s;
         const uint32_t env_id = env_id0 + (uint32_t)i;
-        init_env(L, s, P, env_id, form_base);
+        init_env(L, s, P, env_id);
         for (int k = 0; k < steps; ++k) {
             const size_t slot = (size_t)k * n + i;
-            const StepResult r = (N >= 7) ? v1_step<3>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con, form_base)
-                                 : (N >= 4) ? v1_step<2>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con, form_base)
-                                 : (N >= 2) ? v1_step<1>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con, form_base)
-                                          : v1_step<0>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con, form_base);
-            if (r.done) reset_env(L, s, P, env_id, form_base);
+            const StepResult r = (N >= 7) ? v1_step<3>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con)
+                                 : (N >= 4) ? v1_step<2>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con)
+                                 : (N >= 2) ? v1_step<1>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con)
+                                          : v1_step<0>(L, s, P, env_id, left_actions ? left_actions + slot * 2 * N : nullptr, C, con);
+            if (r.done) reset_env(L, s, P, env_id);
             if (obs) for (int e = 0; e < D; ++e) obs[slot * D + e] = obs_elem(L, N, e);
             if (reward) reward[slot] = r.reward;
             if (done) done[slot] = (uint8_t)r.done;
