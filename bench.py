@@ -472,7 +472,7 @@ def bench_step_api(torch, dev, peak, n=4096, steps=1000):
     return out
 
 
-def bench_v1_rollout(torch, dev, peak, N, n, K=ROLLOUT_K, reps=10):
+def bench_v1_rollout(torch, dev, peak, N, n, K=ROLLOUT_K, reps=10, cpu_seconds=2.0):
     """BASELINE.json configs[4] (5v5 at 2^18 envs) and its siblings: the v1 N-vs-N rigid-body variant, fused K = 64 rollouts
     with given uniform random left-team actions (HBM resident), random right team drawn in-kernel."""
     from gym_futbol_b200 import FutbolV1VecEnv
@@ -489,10 +489,22 @@ def bench_v1_rollout(torch, dev, peak, N, n, K=ROLLOUT_K, reps=10):
     state_bytes = 48 * B + 18                                     # bodies + scalars; the arbiter cache is touched only by contacts
     bpe = (4 + 8 * N) * 4 + 4 + 1 + 2 * N + 2.0 * state_bytes / K
     rate = n * K / (ms * 1e-3)
+    cpu = None
+    if cpu_seconds > 0:                                        # the C restatement (oracle/futbol_v1_oracle.c) on the host cores, as context
+        from oracle.v1 import OracleV1
+        threads = os.cpu_count() or 1
+        orc = OracleV1(2048, seed=0, number_of_player=N)
+        orc.rollout(K, autoreset=2, n_threads=threads, record=False)
+        t0, steps = time.perf_counter(), 0
+        while time.perf_counter() - t0 < cpu_seconds:
+            orc.rollout(K, autoreset=2, n_threads=threads, record=False)
+            steps += 2048 * K
+        cpu = {"value": steps / (time.perf_counter() - t0), "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "2048 envs x %d env-steps, C oracle, %d pthreads (the reference's own v1 needs pymunk, absent here)" % (steps // 2048, threads)}
     out = {"workload": "v1 Futbol %dv%d, %d envs, fused K=%d rollout, given random left actions" % (N, N, n, K), "launches_timed": reps,
            "ms_per_launch": ms, "env_steps_per_s": rate, "bytes_per_env_step": bpe, "hbm_gbs": rate * bpe / 1e9,
            "hbm_frac": rate * bpe / 1e9 / peak, "contacts_per_env_step": st["contacts"] / max(1, st["env_steps"]),
-           "contacts_dropped": st["contacts_dropped"], "arbiter_cache_bytes_per_env": 16 * P,
+           "contacts_dropped": st["contacts_dropped"], "arbiter_cache_bytes_per_env": 16 * P, "cpu_baseline": cpu,
            "note": "latency bound (sequential turns, Gauss-Seidel contact solver, divergent contacts): see profiles/r2_v1_history.md"}
     env.close()
     return out
