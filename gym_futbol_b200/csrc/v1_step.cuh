@@ -4,9 +4,10 @@
 // circle/circle and circle/segment contacts, arbiter pre-step, damped velocity integration with the
 // reference's speed clamps, warm start, ten sequential-impulse iterations.
 //
-// PARITY UNPINNED at the pymunk boundary: the physics restates Chipmunk's published
-// algorithm; what Chipmunk leaves implementation-defined (body order, contact order, ...) is specified in
-// DESIGN.md and implemented identically by the CPU checker, with which this code agrees bit for bit.
+// Parity: the game logic is pinned to traces of the reference's own Python (executed over a pymunk
+// stand-in, tests/golden/v1_golden.npz); the physics at the pymunk boundary is UNPINNED: it restates Chipmunk's published
+// algorithm, and what Chipmunk leaves implementation-defined (body order, contact order, ...) is specified in DESIGN.md
+// and implemented identically by the CPU checker, with which this code agrees bit for bit.
 // Arithmetic: fp64, one IEEE operation per written operation, no FMA contraction.
 //
 // Why one thread per environment and not one warp (players on lanes): the per-environment parallelism is

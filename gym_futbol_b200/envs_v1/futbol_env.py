@@ -7,7 +7,9 @@ does not auto-reset either).  For throughput use ``gym_futbol_b200.FutbolV1VecEn
 
 Differences, all deliberate:
   * the rigid-body physics is this repository's restatement of the Chipmunk2D subset pymunk runs for the
-    reference; parity at that boundary is unpinned (pymunk cannot be run where this was built);
+    reference.  The game logic around it is pinned to traces of the reference's own Python (run over a pymunk
+    stand-in, tests/golden/v1_golden.npz); the contact response itself could not be checked against the real
+    library (pymunk cannot be run where this was built);
   * randomness (right-team actions, pass targets, out-of-bounds receiver, side after a goal) is the seeded
     counter-based Philox stream (``seed=``, ``env_id=``); the reference is unseeded;
   * ``width`` / ``height`` must keep their defaults (the reference's walls, goals and normalisation constants

@@ -240,7 +240,8 @@ class FutbolV1VecEnv(FutbolVecEnv):
     ``step(actions)``: actions uint8 ``[n, 2N]`` = (arrow key, action key) per left-team player, i.e. the
     reference's ``MultiDiscrete([5, 5] * N)`` (:78-79); the right team draws uniform random actions (:429).
     Observations are the normalised ``4 + 8N`` vector (:154-180).  The physics restates the Chipmunk2D subset
-    pymunk runs for the reference; parity at that boundary is unpinned.
+    pymunk runs for the reference: the game logic is pinned to traces of the reference's own Python, the contact physics
+    at the pymunk boundary is a restatement that cannot be checked against the real library here.
     """
 
     STATE_DTYPE = _lib.V1_ENV_STATE

@@ -1,5 +1,5 @@
-"""ctypes binding of the v1 oracle (oracle/futbol_v1_oracle.c).  TEST INFRASTRUCTURE ONLY; parity unpinned
-(see the header of the C file)."""
+"""ctypes binding of the v1 oracle (oracle/futbol_v1_oracle.c).  TEST INFRASTRUCTURE ONLY.  Game logic pinned to traces of
+the reference's own Python (tests/golden/v1_golden.npz), contact physics unpinned (see the header of the C file)."""
 from __future__ import annotations
 
 import ctypes as C

@@ -1,6 +1,7 @@
 """The v1 oracle (CPU restatement of Futbol.step + the Chipmunk subset) against every external pin the
-reference offers.  PARITY UNPINNED: pymunk cannot be run here and the reference has no test at this
-boundary; what CAN be pinned is checked: episode length 300
+reference offers (the traces of the reference's own Python are in tests/test_oracle_v1_golden.py).  The physics at the pymunk
+boundary is UNPINNED: pymunk cannot be run here and the reference has no test at this boundary; what CAN
+be pinned from outside is checked: episode length 300
 (gym_futbol/envs_v1/2v2/logs/evaluations.npz), observation/action shapes (saved-model JSON), kick-off
 formations (team.py:52-112 re-derived independently below), single-body closed forms and restitution.
 """
