@@ -9,6 +9,7 @@
 // Inside a kernel the 6 B doubles sit in shared memory (one column per lane), scalars in registers; the
 // arbiter cache stays in HBM and is touched only by pairs in contact.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 #include "../../include/futbol_b200.h"
 #include "v1_step.cuh"
@@ -290,7 +291,11 @@ static inline int regc_for(int) { return FUTBOL_V1_REGC; }     // tuning builds 
 #else
 static inline int regc_for(int n_players) { return n_players >= 7 ? 3 : (n_players >= 4 ? 2 : (n_players >= 3 ? 1 : 0)); }
 #endif   // contacts kept in registers by the solver (v1_step.cuh space_step)
-static inline int smem_for(int n_players) { return block_smem_bytes(n_players, threads_for(n_players) / 32); }
+static inline int smem_for(int n_players)
+{
+    static const int pad = getenv("FUTBOL_V1_SMEM_PAD") ? atoi(getenv("FUTBOL_V1_SMEM_PAD")) : 0;   // occupancy experiments only
+    return block_smem_bytes(n_players, threads_for(n_players) / 32) + pad;
+}
 
 cudaError_t launch_reset(const V1Params &P, void *state, const uint8_t *mask, void *obs, int obs_f64, int init, cudaStream_t st)
 {
