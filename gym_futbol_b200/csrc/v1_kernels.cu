@@ -289,7 +289,7 @@ static inline int threads_for(int n_players) { return n_players <= 4 ? 64 : 32; 
 #ifdef FUTBOL_V1_REGC
 static inline int regc_for(int) { return FUTBOL_V1_REGC; }     // tuning builds (tools/build_variant.py)
 #else
-static inline int regc_for(int n_players) { return n_players >= 7 ? 3 : (n_players >= 4 ? 2 : (n_players >= 3 ? 1 : 0)); }
+static inline int regc_for(int n_players) { return n_players >= 7 ? 3 : (n_players >= 5 ? 2 : (n_players >= 3 ? 1 : 0)); }
 #endif   // contacts kept in registers by the solver (v1_step.cuh space_step)
 static inline int smem_for(int n_players)
 {

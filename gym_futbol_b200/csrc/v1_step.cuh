@@ -394,9 +394,9 @@ __device__ __forceinline__ void warm_start_contact(Lane L, const Contact &k, int
 // The first REGC contacts of a step live in registers (c0, c1, c2), the rest in the local-memory list `con` (index
 // i - REGC): a step rarely has more than two, and the ten solver iterations would otherwise wait on local-memory
 // loads (L1 is small next to 200 KB of shared memory: ncu showed 53 % of the long-scoreboard stalls there).
-// REGC = how many contacts are register-resident, chosen by measurement (end of round 1, env-steps/s): 0 for 1v1 (one
-// costs 2 %), 1 for N = 2, 3 (a second one costs occupancy: 2v2 -20 %), 2 for N = 4 ... 6, 3 for N >= 7 (+3 % at 7v7 and
-// 10v10, -1 % at 5v5).
+// REGC = how many contacts are register-resident, chosen by measurement (end of round 2, env-steps/s, tools/exp_variants_v1.sh):
+// 0 for 1v1 and 2v2 (with a register cap, v1_kernels.cu), 1 for 3v3 and 4v4 (4v4: +4 % over 2), 2 for 5v5 and 6v6
+// (5v5: 0 -8 %, 1 +0.3 %, 3 -15 %), 3 for N >= 7.
 template <int REGC>
 __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, const PairCache &C, Contact *con, int &overflow)
 {
