@@ -50,6 +50,9 @@ constexpr double kSqLe1 = 0x1.0000000000001p+0;
 constexpr double kSqLe2 = 0x1.0000000000001p+2;
 constexpr double kSqGt12 = 144.0;
 constexpr double kSqLt1 = 1.0, kSqLt4 = 16.0;
+// random() = k * 2^-24 (k = w >> 8, exact in double):  random() < 0.9  <=>  k <= 15099494;  random() < 0.05  <=>  k <= 838860;
+// random() > 0.8  <=>  k >= 13421773
+constexpr uint32_t kULt0p9 = 15099494u, kULt0p05 = 838860u, kUGt0p8 = 13421773u;
 // products of reference constants, rounded once as the reference's float64 multiply rounds them
 // (__dmul_rn is not folded by the compiler; tests/test_sqrt_thresholds.py::test_constant_products)
 constexpr double kWid02 = 13.600000000000001;   // width * 0.2, :895
@@ -250,7 +253,9 @@ __device__ __forceinline__ void player_turn(Lane L, uint32_t &j, V0Regs &s, cons
     // one more draw in: has-ball run (:353), shoot (:367), assist (:416); no-ball intercept (:459, even when far)
     const uint32_t w = L.draw(j);
     j += (has_ball != is_int) ? 1u : 0u;
-    const double u = (double)(w >> 8) * (1.0 / 16777216.0);
+    // random() = k * 2^-24 with k = w >> 8: the fixed thresholds are integer compares on k (kU* below, exact:
+    // tests/test_sqrt_thresholds.py); the double is only formed where a computed chance is compared
+    const uint32_t uk = w >> 8;
 
     const double bx = dsub(ball_x, ax), by = dsub(ball_y, ay);           // :432
     const double vx = hb_assist ? dsub(mx, ball_x) : bx;                 // :412
@@ -262,11 +267,14 @@ __device__ __forceinline__ void player_turn(Lane L, uint32_t &j, V0Regs &s, cons
     const double q = sqsum(bx, by);
     const bool lt1 = q < kSqLt1, le2 = q <= kSqLe2, free_ball = s.owner == kNoOne;
     const bool mid = nb_int && !lt1 && le2 && !free_ball;
-    double chance_mid = 0.0;
-    if (mid) chance_mid = dmul(-0.9, dsub(fsqrt(q), 2.0));               // q in [1, 4]: inside the guard-free sqrt's domain
-    const bool take = nb_int && ((free_ball && q < kSqLt4) || (lt1 ? u < 0.9 : (mid && u < chance_mid)));
+    bool take_mid = false;
+    if (mid) {                                                           // q in [1, 4]: inside the guard-free sqrt's domain
+        const double chance_mid = dmul(-0.9, dsub(fsqrt(q), 2.0));
+        take_mid = (double)uk * (1.0 / 16777216.0) < chance_mid;
+    }
+    const bool take = nb_int && ((free_ball && q < kSqLt4) || (lt1 ? uk <= kULt0p9 : take_mid));
     // has-ball run, :353-356 (Q3)
-    const bool drop = hb_run && u < 0.05;
+    const bool drop = hb_run && uk <= kULt0p05;
     const bool carry = hb_run && !drop;
 
     // the player's own row after the turn (Q4: a no-ball intercept keeps the previous vector and speed;
@@ -374,7 +382,7 @@ __device__ __forceinline__ int easy_action(Lane L, uint32_t &j, int a, bool has_
     // the draw happens only when the geometric clause holds (short-circuit `and`, :81-85)
     const uint32_t w = L.draw(j);
     j += (has_ball && !in_range && open_mate) ? 1u : 0u;
-    const bool lucky = (double)(w >> 8) * (1.0 / 16777216.0) > 0.8;
+    const bool lucky = (w >> 8) >= kUGt0p8;                              // random() > 0.8
     const bool far_mate = sqsum(dsub(mx, ax), dsub(my, ay)) > kSqGt12;                         // distance > 12
     const bool ball_close = sqsum(dsub(L.f(bo + kX), ax), dsub(L.f(bo + kY), ay)) <= kSqLe1;  // distance <= 1.0, :90
     const int with_ball = in_range ? (int)kShoot : ((open_mate && lucky && far_mate) ? (int)kAssist : (int)kRun);

@@ -60,3 +60,10 @@ def test_constant_products():
     assert 68 * 0.2 == 13.600000000000001 and 68 * 0.8 == 54.400000000000006 and 105 * 0.1 == 10.5
     assert 105 * 0.6 == 63.0 and 105 * 0.75 == 78.75 and 68 * 0.5 == 34.0
     assert -50 * 0.3 == -15.0 and 60 * 0.3 == 18.0 and 30 * 0.3 == 9.0 and 0.9 / (1.0 - 2.0) == -0.9
+
+
+def test_uniform_thresholds_as_integer_compares():
+    """v0_step.cuh kU*: random() = k * 2**-24 (exact in float64); the reference's fixed thresholds as compares on k."""
+    for k in list(range(15099494 - 70, 15099494 + 70)) + list(range(838860 - 70, 838860 + 70)) + list(range(13421773 - 70, 13421773 + 70)) + [0, 1, (1 << 24) - 1]:
+        u = k * 2.0 ** -24
+        assert (u < 0.9) == (k <= 15099494) and (u < 0.05) == (k <= 838860) and (u > 0.8) == (k >= 13421773)
