@@ -304,7 +304,7 @@ __device__ __forceinline__ void rollout_span(const V0Params &P, const StateView 
             }
         };
 #ifndef FUTBOL_SLICED_LAYOUT
-#define FUTBOL_SLICED_LAYOUT 1
+#define FUTBOL_SLICED_LAYOUT 8
 #endif
 #ifndef FUTBOL_PLAIN_LAYOUT
 #define FUTBOL_PLAIN_LAYOUT 0
@@ -505,9 +505,12 @@ V0RolloutChoice v0_plan_rollout(const V0Params &P, int K, int slices, int varian
     const int slots = P.random_opp ? rollout_block_slots<true>() : rollout_block_slots<false>();
     int n = 1;
     if (slices > 0) n = slices < K ? slices : K;
-    else if (groups > slots && groups < 2 * slots) {
-        n = (11 * slots + 2 * groups - 1) / (2 * groups);          // five to six waves of units
-        if (n > K / 4) n = K / 4;
+    else if (groups > slots) {      // measured per wave count, profiles/r2_slices.md ("Slices per wave count")
+        const long long g = groups, sl = slots;
+        if (g < 2 * sl) n = (int)((11 * sl + 2 * g - 1) / (2 * g));     // one to two waves: five to six waves of units
+        else if (g <= 6 * sl) n = 3;
+        else if (g <= 10 * sl) n = 2;
+        if (n > K / 4) n = K / 4 > 0 ? K / 4 : 1;
     }
     if (n > 1) {
         const int chunk_steps = (K + n - 1) / n;

@@ -366,8 +366,7 @@ __device__ __forceinline__ void resolve_pass(Lane L, const PendingShot &shot)
     L.f(bo + kSP) = dadd(lo, dmul(dsub(hi, lo), u));                     // random.uniform
 }
 
-// the same, out of line: the time-sliced rollout kernel runs 1.3 % faster with the pass resolved through a call (and the
-// plain kernel 1.3 % slower): code layout in an instruction-fetch-bound loop, measured (profiles/r2_v0_history.md)
+// the same, out of line (LAYOUT bits 0 / 1): layouts measured in profiles/r2_v0_history.md (r2d, r2e, r2g); not in the shipped kernels
 static __device__ __noinline__ void resolve_pass_outlined(Lane L, const PendingShot &shot) { resolve_pass(L, shot); }
 static __device__ __noinline__ void resolve_shot_outlined(Lane L, const V0Regs &s, const V0Params &P, bool random_opp, uint32_t env_id,
                                                           const PendingShot &shot) { resolve_shot(L, s, P, random_opp, env_id, shot); }
@@ -412,8 +411,25 @@ __device__ __forceinline__ void advance_xy(Lane L, int src, double &xo, double &
 // The kinematics phase, :661-663: all five rows in one straight-line block (independent rows: the scheduler
 // overlaps their sqrt / reciprocal chains).  4.6 KB of code; a rolled loop over one out-of-line copy fits the
 // instruction cache better (hit rate 94.5 % -> 99.4 %) but is 3 % slower for the lost overlap (r1_history.md, r1i).
+// PAIRS: two trips over a pair of player rows + the ball row -- 3/5 of the code, two chains still overlap.  The time-sliced
+// kernel runs 1.7 % faster with it, the plain kernel 1.2 % slower (profiles/r2_v0_history.md, r2g).
+template <bool PAIRS = false>
 __device__ __forceinline__ void advance_all(Lane L)
 {
+    if (PAIRS) {
+#pragma unroll 1
+        for (int p = 0; p < 2; ++p) {
+            const int r0 = 2 * p * kRowStride, r1 = r0 + kRowStride;
+            double ax, ay, bx, by;
+            advance_xy(L, r0, ax, ay);
+            advance_xy(L, r1, bx, by);
+            L.f(r0 + kX) = ax; L.f(r0 + kY) = ay; L.f(r1 + kX) = bx; L.f(r1 + kY) = by;
+        }
+        double cx, cy;
+        advance_xy(L, kBallRow * kRowStride, cx, cy);
+        L.f(kBallRow * kRowStride + kX) = cx; L.f(kBallRow * kRowStride + kY) = cy;
+        return;
+    }
     double nx[5], ny[5];
 #pragma unroll
     for (int r = 0; r < 5; ++r) advance_xy(L, r * kRowStride, nx[r], ny[r]);
@@ -444,7 +460,8 @@ struct StepResult { double reward; int done; int flags; };
 // randint(0, 15) draw is not taken.
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
 // LAYOUT (code layout of the rare / repeated parts; results are identical): bit 0 = the pending pass resolved through a call,
-// bit 1 = the pending shot resolved through a call, bit 2 = the five kinematics rows through one out-of-line copy
+// bit 1 = the pending shot resolved through a call, bit 2 = the five kinematics rows through one out-of-line copy,
+// bit 3 = the kinematics as two trips over a pair of player rows + the ball row
 template <bool RANDOM_OPP, typename Hook = NoHook, int LAYOUT = 0>
 __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params &P, uint32_t env_id, int ai_action, int opp_action = -1,
                                               Hook before_draw_store = Hook())
@@ -550,7 +567,7 @@ __device__ __forceinline__ StepResult v0_step(Lane L, V0Regs &s, const V0Params 
     if (LAYOUT & 4) {
 #pragma unroll 1
         for (int r = 0; r < 5; ++r) { const XY n = advance_row(L, r * kRowStride); L.f(r * kRowStride + kX) = n.x; L.f(r * kRowStride + kY) = n.y; }
-    } else advance_all(L);
+    } else advance_all<(LAYOUT & 8) != 0>(L);
 
     // ---- _get_reward, :752-861 (evaluated before the goal re-kickoff) ----
     const double ball_x = L.f(bo + kX), ball_y = L.f(bo + kY);

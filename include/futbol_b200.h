@@ -180,7 +180,7 @@ uint64_t futbol_launch_count(const FutbolHandle *h);
  * futbol_rollout on a batch of only a few waves of thread blocks (e.g. 131,072 envs: one of eight ranks of the 2^20 job)
  * cuts the K steps into time slices and lets a grid that just fills the GPU take (slice, env-block) units from a queue,
  * so that no SM idles through a partial last wave.  Results do not depend on the slicing.  slices: 0 = chosen per
- * launch from the batch size (default: sliced between one and two waves of blocks), 1 = never slice, n > 1 = n equal
+ * launch from the batch size (default: sliced from one to ten waves of thread blocks), 1 = never slice, n > 1 = n equal
  * slices.  v0 only; ignored for v1.  No reference counterpart. */
 int futbol_set_rollout_slices(FutbolHandle *h, int slices);
 /* the number of time slices futbol_rollout will use for K steps on the current device (1 = the plain kernel) */

@@ -135,8 +135,8 @@ def test_dense_kernel_equals_standard(n, K, random_opp):
 
 
 def test_automatic_kernel_choice():
-    """Sliced between one and two waves of blocks (one rank of eight of the 2^20 job), plain otherwise; the dense kernel only
-    on request."""
+    """Plain up to one wave of blocks and beyond ten, time-sliced in between (4 slices at one rank of eight of the 2^20 job, 3
+    from two to six waves, 2 up to ten: profiles/r2_slices.md); the dense kernel only on request."""
     from gym_futbol_b200 import FutbolVecEnv
     assert FutbolVecEnv(4096, seed=0).rollout_kernel(64) == "v0_rollout_kernel"          # under one wave
     env = FutbolVecEnv(131072, seed=0)
@@ -145,4 +145,6 @@ def test_automatic_kernel_choice():
     assert env.rollout_kernel(64) == "v0_rollout_kernel"
     env.set_rollout_variant(2)
     assert env.rollout_kernel(64) == "v0_rollout_dense_kernel"
-    assert FutbolVecEnv(262144, seed=0).rollout_kernel(64) == "v0_rollout_kernel"        # 2.8 waves: plain wins
+    env = FutbolVecEnv(262144, seed=0)                                                   # 2.8 waves: three slices
+    assert env.rollout_kernel(64) == "v0_rollout_sliced_kernel" and env.rollout_slices(64) == 3
+    assert FutbolVecEnv(1 << 20, seed=0).rollout_kernel(64) == "v0_rollout_kernel"       # 11 waves: plain
