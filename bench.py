@@ -360,6 +360,7 @@ def main():
                          ("v1_2v2_2p20", lambda: bench_v1_rollout(torch, dev, peak, 2, 1 << 20)),
                          ("v1_5v5_2p18", lambda: bench_v1_rollout(torch, dev, peak, 5, 1 << 18)),
                          ("v1_10v10_2p16", lambda: bench_v1_rollout(torch, dev, peak, 10, 1 << 16)),
+                         ("v1_5v5_2p18_k256", lambda: bench_v1_rollout(torch, dev, peak, 5, 1 << 18, K=256, reps=4, cpu_seconds=0.0)),
                          ("ppo_65536", lambda: bench_ppo(torch, dev))):
             try:
                 configs[name] = fn()
@@ -479,10 +480,19 @@ def bench_v1_rollout(torch, dev, peak, N, n, K=ROLLOUT_K, reps=10, cpu_seconds=2
     env = FutbolV1VecEnv(n, number_of_player=N, device=dev, seed=0)
     env.reset()
     acts = torch.randint(0, 5, (K, n, 2 * N), dtype=torch.uint8, device=dev)
+    kernel, slices = env.rollout_kernel(K), env.rollout_slices(K)
     for _ in range(3):
         env.rollout(K, actions=acts)
     env.read_stats(clear=True)
-    ms = _timed(torch, lambda: env.rollout(K, actions=acts), reps)
+    # the automatic launch and, for the record, the plain launch of the same batch, alternating (the envs' episodes run in
+    # step, so the cost of a step depends on where in the episode the launch falls: both see the same mix)
+    ms = ms_plain = 0.0
+    for _ in range(reps):
+        env.set_rollout_slices(0)
+        ms += _timed(torch, lambda: env.rollout(K, actions=acts), 1) / reps
+        env.set_rollout_slices(1)
+        ms_plain += _timed(torch, lambda: env.rollout(K, actions=acts), 1) / reps
+    env.set_rollout_slices(0)
     st = env.read_stats()
     B = 2 * N + 1
     P = B * (B - 1) // 2 + 12 * B
@@ -502,6 +512,7 @@ def bench_v1_rollout(torch, dev, peak, N, n, K=ROLLOUT_K, reps=10, cpu_seconds=2
         cpu = {"value": steps / (time.perf_counter() - t0), "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "2048 envs x %d env-steps, C oracle, %d pthreads (the reference's own v1 needs pymunk, absent here)" % (steps // 2048, threads)}
     out = {"workload": "v1 Futbol %dv%d, %d envs, fused K=%d rollout, given random left actions" % (N, N, n, K), "launches_timed": reps,
+           "kernel": kernel, "time_slices": slices, "env_steps_per_s_plain_launch": n * K / (ms_plain * 1e-3),
            "ms_per_launch": ms, "env_steps_per_s": rate, "bytes_per_env_step": bpe, "hbm_gbs": rate * bpe / 1e9,
            "hbm_frac": rate * bpe / 1e9 / peak, "contacts_per_env_step": st["contacts"] / max(1, st["env_steps"]),
            "contacts_dropped": st["contacts_dropped"], "arbiter_cache_bytes_per_env": 16 * P, "cpu_baseline": cpu,

@@ -185,13 +185,13 @@ uint64_t futbol_launch_count(const FutbolHandle *h) { return h ? h->launches : 0
 int futbol_rollout_slices(FutbolHandle *h, int K)
 {
     if (h == nullptr || K <= 0) return fail(FUTBOL_ERR_ARG, "null handle or K <= 0%s");
-    return h->is_v1 ? 1 : v0_plan_rollout(h->v0, K, h->rollout_slices, h->rollout_variant).slices;
+    return h->is_v1 ? v1::plan_rollout_slices(h->v1, K, h->rollout_slices) : v0_plan_rollout(h->v0, K, h->rollout_slices, h->rollout_variant).slices;
 }
 
 int futbol_rollout_kernel(FutbolHandle *h, int K)
 {
     if (h == nullptr || K <= 0) return fail(FUTBOL_ERR_ARG, "null handle or K <= 0%s");
-    if (h->is_v1) return 0;
+    if (h->is_v1) return v1::plan_rollout_slices(h->v1, K, h->rollout_slices) > 1 ? 1 : 0;
     const V0RolloutChoice c = v0_plan_rollout(h->v0, K, h->rollout_slices, h->rollout_variant);
     return c.kernel == 1 ? 2 : (c.slices > 1 ? 1 : 0);
 }
@@ -255,7 +255,7 @@ int futbol_rollout_vs(FutbolHandle *h, void *state, int K, const uint8_t *action
     if (K <= 0) return fail(FUTBOL_ERR_ARG, "K must be positive%s");
     if (!h->initialised) return fail(FUTBOL_ERR_ARG, "futbol_reset must be called before futbol_rollout%s");
     if (h->is_v1 && ((uintptr_t)actions & 1u)) return fail(FUTBOL_ERR_ARG, "v1: the action buffer must be 2-byte aligned%s");
-    cudaError_t e = h->is_v1 ? v1::launch_rollout(h->v1, state, K, actions, opp_actions, obs, reward, done, stats, (cudaStream_t)stream)
+    cudaError_t e = h->is_v1 ? v1::launch_rollout(h->v1, state, K, actions, opp_actions, obs, reward, done, stats, h->rollout_slices, (cudaStream_t)stream)
                              : v0_launch_rollout(h->v0, state, K, actions, opp_actions, obs, reward, done, stats, h->rollout_slices, h->rollout_variant, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     h->launches += 1;

@@ -6,10 +6,12 @@
 //   uint64  t_total[np];  uint32 stamp[np];  int32 ep_step[np];  uint8 owner_side[np], flags[np]
 //   CacheRec cache[P][np]                     the arbiter cache, 16 bytes per shape pair: accumulated normal impulse and
 //                                             the stamp of the space step in which the pair last touched
+//   uint32  sched[64 + np / 32]               work queue of the time-sliced rollout (zeroed by the launcher)
 // Inside a kernel the 6 B doubles sit in shared memory (one column per lane), scalars in registers; the
 // arbiter cache stays in HBM and is touched only by pairs in contact.
 #include <cuda_runtime.h>
 #include <stdlib.h>
+#include <mutex>
 #include <stdint.h>
 #include "../../include/futbol_b200.h"
 #include "v1_step.cuh"
@@ -20,15 +22,18 @@ namespace v1 {
 
 struct StateView {
     double *body; uint64_t *t_total; uint32_t *stamp; int32_t *ep_step; uint8_t *owner_side, *flags; CacheRec *cache;
+    uint32_t *sched;      // work queue of the time-sliced rollout: unit counter, then one progress word per warp of envs
     size_t np;
 };
+constexpr int kSchedHead = 64;                                        // words before the per-warp counters (256 B)
+__host__ __device__ inline size_t sched_words(size_t np) { return kSchedHead + np / 32; }
 
 __host__ __device__ inline size_t padded(int n) { return ((size_t)n + 255) & ~(size_t)255; }
 
 size_t state_bytes(int n_envs, int n_players)
 {
     const size_t B = 2 * n_players + 1, P = n_pairs((int)B);
-    return padded(n_envs) * (6 * B * 8 + 8 + 4 + 4 + 1 + 1 + P * sizeof(CacheRec));
+    return padded(n_envs) * (6 * B * 8 + 8 + 4 + 4 + 1 + 1 + P * sizeof(CacheRec)) + sched_words(padded(n_envs)) * 4;
 }
 
 __host__ __device__ inline StateView make_view(void *base, int n, int n_players)
@@ -43,12 +48,21 @@ __host__ __device__ inline StateView make_view(void *base, int n, int n_players)
     v.stamp = (uint32_t *)p;     p += v.np * 4;
     v.ep_step = (int32_t *)p;    p += v.np * 4;
     v.owner_side = (uint8_t *)p; p += v.np;
-    v.flags = (uint8_t *)p;
+    v.flags = (uint8_t *)p;      p += v.np;
+    v.sched = (uint32_t *)p;
     return v;
 }
 
+// CG: loads from L2 (ld.global.cg) -- the time-sliced rollout reads state that a block on another SM wrote in this launch
+template <bool CG = false>
 __device__ __forceinline__ void load_state(const StateView &v, int i, Lane L, V1Regs &s, int B)
 {
+    if (CG) {
+        for (int k = 0; k < 6 * B; ++k) L.f(k * kCol) = __ldcg(v.body + (size_t)k * v.np + i);
+        s.t_total = __ldcg(v.t_total + i); s.stamp = __ldcg(v.stamp + i); s.ep_step = __ldcg(v.ep_step + i);
+        s.owner_side = __ldcg(v.owner_side + i);
+        return;
+    }
     for (int k = 0; k < 6 * B; ++k) L.f(k * kCol) = v.body[(size_t)k * v.np + i];
     s.t_total = v.t_total[i]; s.stamp = v.stamp[i]; s.ep_step = v.ep_step[i]; s.owner_side = v.owner_side[i];
 }
@@ -159,15 +173,15 @@ __global__ void v1_step_kernel(const __grid_constant__ V1Params P, StateView v, 
 // MINB: resident 64-thread blocks per SM the register allocation is capped for.  Measured (tools/exp_variants_v1.sh, end of
 // round 2): the small teams, whose shared-memory state is small, gain from more warps -- 1v1 +3.9 % at 12 blocks (85
 // registers), 2v2 +1.8 % at 10 (102) -- from 3v3 on the uncapped allocation wins.
-template <int REGC, int MINB>
-__global__ void __launch_bounds__(64, MINB) v1_rollout_kernel(const __grid_constant__ V1Params P, StateView v, int K, const uint8_t *__restrict__ actions,
-                                  const uint8_t *__restrict__ opp_actions, float *__restrict__ obs,
-                                  float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
+// Steps [k0, k1) of the rollout for the warp of environments `wg` (envs 32 wg .. 32 wg + 31), run by the calling warp in its
+// own shared-memory columns.  SLICED: the state was written by another block of this launch (loads from L2).
+template <int REGC, bool SLICED>
+__device__ __forceinline__ void v1_rollout_span(const V1Params &P, const StateView &v, int wg, int k0, int k1, const uint8_t *__restrict__ actions,
+                                                const uint8_t *__restrict__ opp_actions, float *__restrict__ obs,
+                                                float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int warp_env0 = i - lane;
-    if (warp_env0 >= P.n_envs) return;
+    const int warp_env0 = wg * 32, i = warp_env0 + lane;          // the caller guarantees warp_env0 < n_envs
     const bool live = i < P.n_envs;
     const int rows_in_warp = min(32, P.n_envs - warp_env0);
     const int N = P.n_players, B = 2 * N + 1, D = obs_dim(N);
@@ -180,14 +194,14 @@ __global__ void __launch_bounds__(64, MINB) v1_rollout_kernel(const __grid_const
     Contact con[kMaxContacts];
 
     V1Regs s;
-    if (live) load_state(v, i, L, s, B);
+    if (live) load_state<SLICED>(v, i, L, s, B);
     else init_env(L, s, P, env_id);
 
     double reward_sum = 0.0;
     uint32_t episodes = 0, goals_l = 0, goals_r = 0, outs = 0, contacts = 0, overflow = 0;
     int last_flags = 0;
 #pragma unroll 1
-    for (int k = 0; k < K; ++k) {
+    for (int k = k0; k < k1; ++k) {
         const size_t slot = (size_t)k * n + (size_t)i;
         StepResult r;
         if (live) {
@@ -225,7 +239,7 @@ __global__ void __launch_bounds__(64, MINB) v1_rollout_kernel(const __grid_const
         }
         if (lane == 0) {
             atomicAdd(&stats->reward_sum, reward_sum);
-            atomicAdd((unsigned long long *)&stats->env_steps, (unsigned long long)rows_in_warp * (unsigned long long)K);
+            atomicAdd((unsigned long long *)&stats->env_steps, (unsigned long long)rows_in_warp * (unsigned long long)(k1 - k0));
             atomicAdd((unsigned long long *)&stats->episodes, (unsigned long long)episodes);
             atomicAdd((unsigned long long *)&stats->goals_ai, (unsigned long long)goals_l);
             atomicAdd((unsigned long long *)&stats->goals_opp, (unsigned long long)goals_r);
@@ -233,6 +247,55 @@ __global__ void __launch_bounds__(64, MINB) v1_rollout_kernel(const __grid_const
             atomicAdd((unsigned long long *)&stats->reserved[0], (unsigned long long)contacts);
             atomicAdd((unsigned long long *)&stats->reserved[1], (unsigned long long)overflow);
         }
+    }
+}
+
+template <int REGC, int MINB>
+__global__ void __launch_bounds__(64, MINB) v1_rollout_kernel(const __grid_constant__ V1Params P, StateView v, int K, const uint8_t *__restrict__ actions,
+                                  const uint8_t *__restrict__ opp_actions, float *__restrict__ obs,
+                                  float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
+{
+    const int wg = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (wg * 32 >= P.n_envs) return;
+    v1_rollout_span<REGC, false>(P, v, wg, 0, K, actions, opp_actions, obs, reward, done, stats);
+}
+
+// The same rollout as a queue of time slices (cf. v0_rollout_sliced_kernel, v0_kernels.cu): a few waves of K-step-long warps
+// leave the SMs idle through the partial last wave (5v5, 2^18 envs: 8192 warps on 1924 slots = 4.26 waves).  The K steps are cut
+// into `chunks` slices; a unit is (slice c, warp of envs g), numbered c * groups + g, and every WARP of a grid that just fills
+// the GPU takes units from a counter (lane 0 + shuffle: no block barrier, no shared memory).  Unit (c, g) needs (c - 1, g),
+// which has a smaller number: it was taken earlier by a warp that is running and never waits on a later unit -- no deadlock
+// whatever the residency.  Hand-over through L2: every lane __threadfence()s after its stores, lane 0 publishes the progress
+// word; the reader polls it, fences, and loads the state and the arbiter-cache records with ld.global.cg.
+template <int REGC, int MINB>
+__global__ void __launch_bounds__(64, MINB) v1_rollout_sliced_kernel(const __grid_constant__ V1Params P, StateView v, int K, int chunk_steps,
+                                  int chunks, int groups, const uint8_t *__restrict__ actions,
+                                  const uint8_t *__restrict__ opp_actions, float *__restrict__ obs,
+                                  float *__restrict__ reward, uint8_t *__restrict__ done, FutbolStats *stats)
+{
+    volatile uint32_t *progress = v.sched + kSchedHead;
+    const uint32_t units = (uint32_t)chunks * (uint32_t)groups;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t mine = 0;
+        if (lane == 0) mine = atomicAdd(v.sched, 1u);
+        // broadcast as a warp reduction: REDUX writes a UNIFORM register, so the compiler knows that the unit -- and every
+        // branch and address derived from it -- is the same in all lanes (a shuffle's result is not: convergence barriers and
+        // vector address arithmetic all over the step, -10 % at 5v5)
+        const uint32_t u = __reduce_add_sync(0xffffffffu, mine);
+        if (u >= units) break;
+        const int c = (int)(u / (uint32_t)groups), g = (int)(u % (uint32_t)groups);
+        if (c > 0) {
+            if (lane == 0) {
+                while (progress[g] < (uint32_t)c) __nanosleep(200);
+                __threadfence();
+            }
+            __syncwarp();
+        }
+        v1_rollout_span<REGC, true>(P, v, g, c * chunk_steps, min(K, (c + 1) * chunk_steps), actions, opp_actions, obs, reward, done, stats);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) progress[g] = (uint32_t)(c + 1);
     }
 }
 
@@ -324,12 +387,84 @@ cudaError_t launch_step(const V1Params &P, void *state, const uint8_t *actions, 
     return cudaGetLastError();
 }
 
+// resident WARPS of the time-sliced rollout kernel on the current device for this team size (queried once per device and size)
+template <int REGC, int MINB>
+static int rollout_warp_slots(int n_players)
+{
+    static std::mutex mu;
+    static int slots[64][kMaxN + 1] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    int &s = slots[dev & 63][n_players];
+    if (s == 0) {
+        int sms = 0, per_sm = 0;
+        const int t = threads_for(n_players);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v1_rollout_sliced_kernel<REGC, MINB>, t, smem_for(n_players));
+        s = sms * per_sm > 0 ? sms * per_sm * (t / 32) : 1;
+    }
+    return s;
+}
+
+static int warp_slots_for(int n_players)
+{
+    const int rc = regc_for(n_players);
+    // register caps of the queue kernel: the plain kernel's residency (REGC 2: 168 registers = 12 warps per SM; REGC 1: 128 = 16)
+    if (rc == 3) return rollout_warp_slots<3, 1>(n_players);
+    if (rc == 2) return rollout_warp_slots<2, 6>(n_players);
+    if (rc == 1) return rollout_warp_slots<1, 8>(n_players);
+    return n_players == 1 ? rollout_warp_slots<0, 12>(n_players) : rollout_warp_slots<0, 10>(n_players);
+}
+
+// Time slices of a K-step rollout of this batch.  slices: 0 = automatic, 1 = never slice, n > 1 = n equal slices
+// (futbol_set_rollout_slices).  Automatic, from the sweep in profiles/r2_v1_history.md ("time slices"), w = warps of envs /
+// resident warps: up to one wave the plain launch (slicing costs 5-12 % there); between one and two waves about eight waves
+// of units (5v5, 65,536 envs: +39 %; 2v2, 131,072: +26 %); four slices up to six waves (5v5 at 2^18 envs, 4.6 waves: +5.8 %;
+// 2^17: +19 %; 2v2 at 2^18: +8.6 %); two slices beyond (2v2 at 2^20 envs, 11 waves: +3 %).
+int plan_rollout_slices(const V1Params &P, int K, int slices)
+{
+    const int groups = blocks_for(P.n_envs, 32);
+    int n = 1;
+    if (slices > 0) n = slices < K ? slices : K;
+    else {
+        const long long g = groups, sl = warp_slots_for(P.n_players);
+        if (g > sl) {
+            if (g < 2 * sl) n = (int)((8 * sl + g - 1) / g);
+            else if (g <= 6 * sl) n = 4;
+            else n = 2;
+        }
+        if (n > K / 4) n = K / 4 > 0 ? K / 4 : 1;
+    }
+    if (n <= 1) return 1;
+    const int chunk_steps = (K + n - 1) / n;
+    return (K + chunk_steps - 1) / chunk_steps;
+}
+
 cudaError_t launch_rollout(const V1Params &P, void *state, int K, const uint8_t *actions, const uint8_t *opp_actions, float *obs,
-                           float *reward, uint8_t *done, FutbolStats *stats, cudaStream_t st)
+                           float *reward, uint8_t *done, FutbolStats *stats, int slices, cudaStream_t st)
 {
     const StateView v = make_view(state, P.n_envs, P.n_players);
     const int t = threads_for(P.n_players), sm = smem_for(P.n_players);
     const int g = blocks_for(P.n_envs, t), rc = regc_for(P.n_players);
+    const int chunks = plan_rollout_slices(P, K, slices);
+    static const bool force_queue = getenv("FUTBOL_V1_FORCE_QUEUE") != nullptr;      // experiments only: one slice through the queue kernel
+    if (chunks > 1 || force_queue) {
+        const int groups = blocks_for(P.n_envs, 32), chunk_steps = (K + chunks - 1) / chunks;
+        cudaError_t e = cudaMemsetAsync(v.sched, 0, sched_words(v.np) * 4, st);
+        if (e != cudaSuccess) return e;
+        const long long unit_blocks = ((long long)chunks * groups + t / 32 - 1) / (t / 32);
+        const long long slot_blocks = warp_slots_for(P.n_players) / (t / 32);
+        const int grid = (int)(unit_blocks < slot_blocks ? unit_blocks : slot_blocks);
+#define FUTBOL_V1_SLICED(RC, MB) v1_rollout_sliced_kernel<RC, MB><<<grid, t, sm, st>>>(P, v, K, chunk_steps, chunks, groups, actions, opp_actions, obs, reward, done, stats)
+        if (rc == 3) FUTBOL_V1_SLICED(3, 1);
+        else if (rc == 2) FUTBOL_V1_SLICED(2, 6);
+        else if (rc == 1) FUTBOL_V1_SLICED(1, 8);
+        else if (P.n_players == 1) FUTBOL_V1_SLICED(0, 12);
+        else FUTBOL_V1_SLICED(0, 10);
+#undef FUTBOL_V1_SLICED
+        return cudaGetLastError();
+    }
     if (rc == 3) v1_rollout_kernel<3, 1><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
     else if (rc == 2) v1_rollout_kernel<2, 1><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);
     else if (rc == 1) v1_rollout_kernel<1, 1><<<g, t, sm, st>>>(P, v, K, actions, opp_actions, obs, reward, done, stats);

@@ -120,7 +120,10 @@ struct PairCache { CacheRec *rec; size_t stride; };
 __device__ __forceinline__ CacheRec cache_load(const PairCache &C, int q)
 {
 #ifndef FUTBOL_HOST_SHIM
-    const double2 raw = *reinterpret_cast<const double2 *>(C.rec + (size_t)q * C.stride);      // one 128-bit load
+    // One 128-bit load through L1.  (The time-sliced rollout hands an env's records from SM to SM: its reader fences after
+    // polling the progress word -- MEMBAR + CCTL.IVALL in SASS, which drops every L1 line of the SM -- so a plain load cannot
+    // see a stale line.  ld.global.cg here instead costs 30-50 % of the whole rollout: profiles/r2_v1_history.md.)
+    const double2 raw = *reinterpret_cast<const double2 *>(C.rec + (size_t)q * C.stride);
     CacheRec r;
     r.jn = raw.x; r.last = (uint32_t)__double2loint(raw.y); r.pad_ = 0;
     return r;

@@ -100,9 +100,9 @@ class FutbolVecEnv:
     ROLLOUT_KERNELS = ("v0_rollout_kernel", "v0_rollout_sliced_kernel", "v0_rollout_dense_kernel")
 
     def rollout_kernel(self, K):
-        """Name of the kernel ``rollout(K)`` launches on this device (v1: always its one rollout kernel)."""
+        """Name of the kernel ``rollout(K)`` launches on this device."""
         if self.act_shape:
-            return "v1_rollout_kernel"
+            return ("v1_rollout_kernel", "v1_rollout_sliced_kernel")[int(self.lib.futbol_rollout_kernel(self._h, int(K)))]
         return self.ROLLOUT_KERNELS[int(self.lib.futbol_rollout_kernel(self._h, int(K)))]
 
     def set_rollout_variant(self, variant):

@@ -181,12 +181,12 @@ uint64_t futbol_launch_count(const FutbolHandle *h);
  * cuts the K steps into time slices and lets a grid that just fills the GPU take (slice, env-block) units from a queue,
  * so that no SM idles through a partial last wave.  Results do not depend on the slicing.  slices: 0 = chosen per
  * launch from the batch size (default: sliced from one to ten waves of thread blocks), 1 = never slice, n > 1 = n equal
- * slices.  v0 only; ignored for v1.  No reference counterpart. */
+ * slices.  v0 and v1 (v1: units are warps of 32 envs).  No reference counterpart. */
 int futbol_set_rollout_slices(FutbolHandle *h, int slices);
 /* the number of time slices futbol_rollout will use for K steps on the current device (1 = the plain kernel) */
 int futbol_rollout_slices(FutbolHandle *h, int K);
-/* which kernel futbol_rollout will launch for K steps on the current device: 0 = standard (20 warps per SM), 1 = standard,
- * time-sliced, 2 = dense (28 warps per SM) */
+/* which kernel futbol_rollout will launch for K steps on the current device: 0 = standard (v0: 20 warps per SM), 1 = standard,
+ * time-sliced, 2 = dense (v0 only: 28 warps per SM) */
 int futbol_rollout_kernel(FutbolHandle *h, int K);
 /* 0 / 1 = the standard kernel (default), 2 = the dense kernel: 7936 B of shared memory per warp and 72 registers, so that a
  * batch of a few waves fills whole waves; measured slower, kept selectable.  Results do not depend on it. */

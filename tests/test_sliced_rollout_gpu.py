@@ -148,3 +148,68 @@ def test_automatic_kernel_choice():
     env = FutbolVecEnv(262144, seed=0)                                                   # 2.8 waves: three slices
     assert env.rollout_kernel(64) == "v0_rollout_sliced_kernel" and env.rollout_slices(64) == 3
     assert FutbolVecEnv(1 << 20, seed=0).rollout_kernel(64) == "v0_rollout_kernel"       # 11 waves: plain
+
+
+# ---- v1: the same queue with warps of 32 envs as units (csrc/v1_kernels.cu, v1_rollout_sliced_kernel) ----
+def _run_v1(N, n, K, reps, slices, seed=13, off=900, given=True):
+    import torch
+    from gym_futbol_b200 import FutbolV1VecEnv
+    env = FutbolV1VecEnv(n, number_of_player=N, seed=seed, env_id_offset=off, total_time=4.0)
+    env.set_rollout_slices(slices)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    outs = []
+    for rep in range(reps):
+        a = torch.randint(0, 5, (K, n, 2 * N), dtype=torch.uint8, device="cuda", generator=g) if given else None
+        o, r, d = env.rollout(K, actions=a)
+        outs.append((o.cpu().numpy().copy(), r.cpu().numpy().copy(), d.cpu().numpy().copy()))
+    torch.cuda.synchronize()
+    return outs, env.get_state(), env.read_stats(), env.rollout_kernel(K)
+
+
+@pytest.mark.parametrize("N,n,K,slices", [(2, 4096 + 77, 64, 4), (5, 2048 + 5, 48, 5), (1, 513, 37, 37), (10, 333, 20, 3),
+                                          (3, 31, 16, 2), (7, 1500, 33, 6)])
+def test_v1_sliced_equals_plain(N, n, K, slices):
+    """Small batches make every unit wait on its predecessor; episodes end inside the rollouts (total_time 4 = 40 steps)."""
+    plain = _run_v1(N, n, K, 3, 1)
+    sliced = _run_v1(N, n, K, 3, slices)
+    assert plain[3] == "v1_rollout_kernel" and sliced[3] == "v1_rollout_sliced_kernel"
+    for (o0, r0, d0), (o1, r1, d1) in zip(plain[0], sliced[0]):
+        assert np.array_equal(o0.view(np.uint32), o1.view(np.uint32))
+        assert np.array_equal(r0.view(np.uint32), r1.view(np.uint32)) and np.array_equal(d0, d1)
+    assert plain[1].tobytes() == sliced[1].tobytes()            # bodies, scalars AND the arbiter cache of every env
+    for key in ("env_steps", "episodes", "goals_ai", "goals_opp", "out_of_field"):
+        assert plain[2][key] == sliced[2][key]
+    assert plain[2]["env_steps"] == 3 * n * K
+
+
+def test_v1_sliced_synthetic_actions():
+    """actions=None (Philox stream 1 inside the kernel) through the sliced launch."""
+    plain = _run_v1(5, 1000, 40, 2, 1, given=False)
+    sliced = _run_v1(5, 1000, 40, 2, 4, given=False)
+    for (o0, r0, d0), (o1, r1, d1) in zip(plain[0], sliced[0]):
+        assert np.array_equal(o0.view(np.uint32), o1.view(np.uint32)) and np.array_equal(r0.view(np.uint32), r1.view(np.uint32))
+        assert np.array_equal(d0, d1)
+    assert plain[1].tobytes() == sliced[1].tobytes()
+
+
+def test_v1_automatic_slices():
+    """Plain up to one wave of warps, time-sliced beyond (BASELINE configs[4], 5v5 at 2^18 envs: 4 slices), same results."""
+    import torch
+    from gym_futbol_b200 import FutbolV1VecEnv
+    assert FutbolV1VecEnv(4096, number_of_player=5, seed=0).rollout_kernel(64) == "v1_rollout_kernel"
+    env = FutbolV1VecEnv(1 << 18, number_of_player=5, seed=0)
+    assert env.rollout_kernel(64) == "v1_rollout_sliced_kernel" and env.rollout_slices(64) == 4
+    assert FutbolV1VecEnv(1 << 20, number_of_player=2, seed=0).rollout_slices(64) == 2
+    n, K = 80000, 32                                            # 2500 warps on ~1776 slots at 5v5: sliced automatically
+    outs = []
+    for slices in (0, 1):
+        e = FutbolV1VecEnv(n, number_of_player=5, seed=3, total_time=2.0)
+        e.set_rollout_slices(slices)
+        e.reset()
+        assert (e.rollout_kernel(K) == "v1_rollout_sliced_kernel") == (slices == 0)
+        o, r, d = e.rollout(K)
+        outs.append((o.clone(), r.clone(), d.clone(), e.get_state().tobytes()))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0].view(torch.int32), outs[1][0].view(torch.int32)) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3]

@@ -1,5 +1,5 @@
 """Times the fused v1 rollout kernel alone (CUDA events, warm): env-steps/s.
-    python tools/time_rollout_v1.py [number_of_player] [n_envs] [K] [reps]"""
+    python tools/time_rollout_v1.py [number_of_player] [n_envs] [K] [reps]        (SLICES=n: futbol_set_rollout_slices, default automatic)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,6 +10,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 18
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 env = FutbolV1VecEnv(n, number_of_player=N, seed=0)
+env.set_rollout_slices(int(os.environ.get("SLICES", "0")))
 env.reset()
 acts = torch.randint(0, 5, (K, n, 2 * N), dtype=torch.uint8, device="cuda")
 for _ in range(2):
@@ -23,6 +24,6 @@ b.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(b) / reps
 st = env.read_stats()
-print("v1 %dv%d n=%d K=%d: %.3f ms/rollout, %.3e env-steps/s; contacts/env-step %.3f, dropped %d, goals %d/%d, outs %d" % (
-    N, N, n, K, ms, n * K / ms * 1e3, st["contacts"] / max(1, st["env_steps"]), st["contacts_dropped"], st["goals_ai"], st["goals_opp"],
+print("v1 %dv%d n=%d K=%d slices=%d: %.3f ms/rollout, %.3e env-steps/s; contacts/env-step %.3f, dropped %d, goals %d/%d, outs %d" % (
+    N, N, n, K, env.rollout_slices(K), ms, n * K / ms * 1e3, st["contacts"] / max(1, st["env_steps"]), st["contacts_dropped"], st["goals_ai"], st["goals_opp"],
     st["out_of_field"]), flush=True)
