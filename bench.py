@@ -497,7 +497,7 @@ def bench_v1_rollout(torch, dev, peak, N, n, K=ROLLOUT_K, reps=10, cpu_seconds=2
     B = 2 * N + 1
     P = B * (B - 1) // 2 + 12 * B
     state_bytes = 48 * B + 18                                     # bodies + scalars; the arbiter cache is touched only by contacts
-    bpe = (4 + 8 * N) * 4 + 4 + 1 + 2 * N + 2.0 * state_bytes / K
+    bpe = (4 + 8 * N) * 4 + 4 + 1 + 2 * N + 2.0 * state_bytes / K   # of the plain launch: the fraction below does not credit hand-overs
     rate = n * K / (ms * 1e-3)
     cpu = None
     if cpu_seconds > 0:                                        # the C restatement (oracle/futbol_v1_oracle.c) on the host cores, as context
@@ -512,7 +512,7 @@ def bench_v1_rollout(torch, dev, peak, N, n, K=ROLLOUT_K, reps=10, cpu_seconds=2
         cpu = {"value": steps / (time.perf_counter() - t0), "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "2048 envs x %d env-steps, C oracle, %d pthreads (the reference's own v1 needs pymunk, absent here)" % (steps // 2048, threads)}
     out = {"workload": "v1 Futbol %dv%d, %d envs, fused K=%d rollout, given random left actions" % (N, N, n, K), "launches_timed": reps,
-           "kernel": kernel, "time_slices": slices, "env_steps_per_s_plain_launch": n * K / (ms_plain * 1e-3),
+           "kernel": kernel, "time_slices": slices, "bytes_per_env_step_with_handover": bpe + 2.0 * state_bytes * (slices - 1) / K, "env_steps_per_s_plain_launch": n * K / (ms_plain * 1e-3),
            "ms_per_launch": ms, "env_steps_per_s": rate, "bytes_per_env_step": bpe, "hbm_gbs": rate * bpe / 1e9,
            "hbm_frac": rate * bpe / 1e9 / peak, "contacts_per_env_step": st["contacts"] / max(1, st["env_steps"]),
            "contacts_dropped": st["contacts_dropped"], "arbiter_cache_bytes_per_env": 16 * P, "cpu_baseline": cpu,

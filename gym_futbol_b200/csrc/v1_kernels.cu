@@ -420,8 +420,9 @@ static int warp_slots_for(int n_players)
 // Time slices of a K-step rollout of this batch.  slices: 0 = automatic, 1 = never slice, n > 1 = n equal slices
 // (futbol_set_rollout_slices).  Automatic, from the sweep in profiles/r2_v1_history.md ("time slices"), w = warps of envs /
 // resident warps: up to one wave the plain launch (slicing costs 5-12 % there); between one and two waves about eight waves
-// of units (5v5, 65,536 envs: +39 %; 2v2, 131,072: +26 %); four slices up to six waves (5v5 at 2^18 envs, 4.6 waves: +5.8 %;
-// 2^17: +19 %; 2v2 at 2^18: +8.6 %); two slices beyond (2v2 at 2^20 envs, 11 waves: +3 %).
+// of units (5v5, 65,536 envs: +39 %; 2v2, 131,072: +26 %); four slices up to four waves (5v5 at 2^17 envs, 2.3 waves: +19 %;
+// 2v2 at 2^18: +8.6 %); two slices beyond (5v5 at 2^18 envs, 4.6 waves: +5.2 % -- four slices would give +5.8 % for twice the
+// extra state traffic; 2v2 at 2^20 envs, 11 waves: +3 %).
 int plan_rollout_slices(const V1Params &P, int K, int slices)
 {
     const int groups = blocks_for(P.n_envs, 32);
@@ -431,7 +432,7 @@ int plan_rollout_slices(const V1Params &P, int K, int slices)
         const long long g = groups, sl = warp_slots_for(P.n_players);
         if (g > sl) {
             if (g < 2 * sl) n = (int)((8 * sl + g - 1) / g);
-            else if (g <= 6 * sl) n = 4;
+            else if (g < 4 * sl) n = 4;
             else n = 2;
         }
         if (n > K / 4) n = K / 4 > 0 ? K / 4 : 1;

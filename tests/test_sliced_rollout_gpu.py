@@ -194,12 +194,13 @@ def test_v1_sliced_synthetic_actions():
 
 
 def test_v1_automatic_slices():
-    """Plain up to one wave of warps, time-sliced beyond (BASELINE configs[4], 5v5 at 2^18 envs: 4 slices), same results."""
+    """Plain up to one wave of warps, time-sliced beyond (BASELINE configs[4], 5v5 at 2^18 envs: 2 slices), same results."""
     import torch
     from gym_futbol_b200 import FutbolV1VecEnv
     assert FutbolV1VecEnv(4096, number_of_player=5, seed=0).rollout_kernel(64) == "v1_rollout_kernel"
     env = FutbolV1VecEnv(1 << 18, number_of_player=5, seed=0)
-    assert env.rollout_kernel(64) == "v1_rollout_sliced_kernel" and env.rollout_slices(64) == 4
+    assert env.rollout_kernel(64) == "v1_rollout_sliced_kernel" and env.rollout_slices(64) == 2
+    assert FutbolV1VecEnv(1 << 17, number_of_player=5, seed=0).rollout_slices(64) == 4
     assert FutbolV1VecEnv(1 << 20, number_of_player=2, seed=0).rollout_slices(64) == 2
     n, K = 80000, 32                                            # 2500 warps on ~1776 slots at 5v5: sliced automatically
     outs = []
