@@ -9,8 +9,7 @@ n = int(os.environ.get("PROF_ENVS", 1 << 18))
 K = int(os.environ.get("PROF_K", 64))
 env = FutbolV1VecEnv(n, number_of_player=N, seed=0)
 env.reset()
-acts = torch.randint(0, 5, (K, n, 2 * N), dtype=torch.uint8, device="cuda")
 for _ in range(int(os.environ.get("PROF_LAUNCHES", 4))):
-    env.rollout(K, actions=acts)
+    env.rollout(K, actions=torch.randint(0, 5, (K, n, 2 * N), dtype=torch.uint8, device="cuda"))     # a fresh table per launch
 torch.cuda.synchronize()
 print("ok", env.read_stats())

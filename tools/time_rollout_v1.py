@@ -12,14 +12,18 @@ reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 env = FutbolV1VecEnv(n, number_of_player=N, seed=0)
 env.set_rollout_slices(int(os.environ.get("SLICES", "0")))
 env.reset()
-acts = torch.randint(0, 5, (K, n, 2 * N), dtype=torch.uint8, device="cuda")
+# distinct action tables, cycled (TABLES=1: one table reused every launch -- each player then repeats its K actions for ever,
+# players pile up at the walls and a step has ~30 % more contacts; the numbers in profiles/ before r2i were taken that way)
+T = int(os.environ.get("TABLES", "8"))
+tables = [torch.randint(0, 5, (K, n, 2 * N), dtype=torch.uint8, device="cuda") for _ in range(T)]
+turn = 0
 for _ in range(2):
-    env.rollout(K, actions=acts)
+    env.rollout(K, actions=tables[turn % T]); turn += 1
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
 for _ in range(reps):
-    env.rollout(K, actions=acts)
+    env.rollout(K, actions=tables[turn % T]); turn += 1
 b.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(b) / reps
