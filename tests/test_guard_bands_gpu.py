@@ -112,14 +112,15 @@ def test_v0_kernels_stay_inside_their_buffers(random_opp, n, K, slices):
     assert _same(torch, runs[0], runs[2]) and _same(torch, runs[1], runs[3])
 
 
-@pytest.mark.parametrize("N,n,K", [(1, 70, 16), (2, 70, 16), (3, 33, 8), (5, 70, 16), (10, 45, 12)])
-def test_v1_kernels_stay_inside_their_buffers(N, n, K):
+@pytest.mark.parametrize("N,n,K,slices", [(1, 70, 16, 1), (2, 70, 16, 4), (3, 33, 8, 1), (5, 70, 16, 3), (10, 45, 12, 12), (2, 2049, 16, 3)])
+def test_v1_kernels_stay_inside_their_buffers(N, n, K, slices):
     import torch
     from gym_futbol_b200 import FutbolV1VecEnv
     runs = []
     for guarded in (True, False):
         for dtype in (torch.float32, torch.float64):
             env = FutbolV1VecEnv(n, number_of_player=N, seed=5, env_id_offset=9, total_time=1.0, dtype=dtype)
+            env.set_rollout_slices(slices)                      # > 1: the work-queue kernel and its scheduler words in the state buffer
             arena = Arena(torch, 64 << 20) if guarded else None
             if guarded:
                 _guarded(env, arena)
