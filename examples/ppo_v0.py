@@ -10,7 +10,8 @@ policy ([256, 256] shared, [128, 128] policy / value heads, colab_notebook.ipynb
 The policy needs obs_t to pick a_t, so the rollout uses the per-step API (one launch per step, state round-trips
 HBM), replayed as one CUDA graph from the second iteration on.  With ``--fused 1`` (default) the step kernel writes
 observation, reward and done flag of step t STRAIGHT into row t + 1 / t of the rollout buffers (``step(out=...)``:
-no per-step copies), and every minibatch is built by ONE gather launch over the six buffers
+no per-step copies), the action and its log-probability come straight from the logits in ONE launch
+(``rollout_buffer.sample_actions``), and every minibatch is built by ONE gather launch over the six buffers
 (``rollout_buffer.gather_minibatch``); ``--fused 0`` is the previous flow (copy the env's buffers every step, six torch
 indexing launches per minibatch) kept for the before/after number.  GAE runs on the device (futbol_gae).  Prints
 env-steps/s of the rollout alone and of rollout + update.  torch is the policy / optimiser library here; the
@@ -27,7 +28,7 @@ import torch
 import torch.nn as nn
 
 from gym_futbol_b200 import FutbolVecEnv
-from gym_futbol_b200.rollout_buffer import gae, gather_minibatch
+from gym_futbol_b200.rollout_buffer import gae, gather_minibatch, sample_actions
 
 
 class Policy(nn.Module):
@@ -47,11 +48,17 @@ class Policy(nn.Module):
 class PPO:
     """Collection (T x (policy forward, sampling, env step) + GAE) and the clipped-surrogate update."""
 
-    def __init__(self, n_envs=65536, n_steps=128, minibatches=4, epochs=4, seed=0, device="cuda:0", bf16=True, fused=True, graph=True):
+    def __init__(self, n_envs=65536, n_steps=128, minibatches=4, epochs=4, seed=0, device="cuda:0", bf16=True, fused=True, graph=True,
+                 sampler=None):
         self.dev = dev = torch.device(device)
         torch.manual_seed(seed)
         torch.backends.cuda.matmul.allow_tf32 = True      # the policy is library code; the simulator stays fp64
         self.n, self.T, self.minibatches, self.epochs, self.fused, self.use_graph = n_envs, n_steps, minibatches, epochs, bool(fused), bool(graph)
+        # "kernel": actions and their log-probabilities straight from the logits in one launch (futbol_sample_actions, the fused
+        # flow's default); "torch": log_softmax + multinomial + gather + cast
+        self.sampler = sampler or ("kernel" if fused else "torch")
+        self.seed = seed
+        self.t_base = torch.zeros(1, dtype=torch.int64, device=dev)   # device counter of the sampler: advanced inside the graph
         n, T = n_envs, n_steps
         self.env = FutbolVecEnv(n, device=dev, seed=seed, random_opp=False)
         self.policy = Policy().to(dev)
@@ -83,10 +90,13 @@ class PPO:
                 with self.amp():
                     logits, v = policy(obs)
                 self.val_buf[t] = v.float()
-                logp_all = torch.log_softmax(logits.float(), dim=-1)
-                a = torch.multinomial(logp_all.exp(), 1).squeeze(-1)
-                self.act_buf[t] = a.to(torch.uint8)
-                self.logp_buf[t] = logp_all.gather(1, a.unsqueeze(1)).squeeze(1)
+                if self.sampler == "kernel":
+                    sample_actions(logits, seed=self.seed, t=t, t_base=self.t_base, out=(self.act_buf[t], self.logp_buf[t]))
+                else:
+                    logp_all = torch.log_softmax(logits.float(), dim=-1)
+                    a = torch.multinomial(logp_all.exp(), 1).squeeze(-1)
+                    self.act_buf[t] = a.to(torch.uint8)
+                    self.logp_buf[t] = logp_all.gather(1, a.unsqueeze(1)).squeeze(1)
                 if self.fused:      # the kernel writes row t + 1 of the observation buffer and row t of reward / done itself
                     obs, _, _, _ = env.step(self.act_buf[t], out=(self.obs_buf[t + 1], self.rew_buf[t], self.done_buf[t]))
                     assert obs.data_ptr() == self.obs_buf[t + 1].data_ptr()
@@ -97,6 +107,7 @@ class PPO:
                     self.done_buf[t].copy_(done)
             with self.amp():
                 self.val_buf[T] = policy(obs)[1].float()
+            self.t_base += T                                   # the next collection (or graph replay) draws fresh numbers
             gae(self.rew_buf, self.done_buf, self.val_buf, 0.99, 0.95, out=(self.adv, self.ret))
 
     def prepare_graph(self):

@@ -56,7 +56,7 @@ EXPORTS = ("futbol_create", "futbol_destroy", "futbol_last_error", "futbol_abi_v
            "futbol_rollout", "futbol_env_state_bytes", "futbol_get_state", "futbol_set_state",
            "futbol_launch_count", "futbol_gae", "futbol_selftest_arith", "futbol_step_vs", "futbol_rollout_vs",
            "futbol_set_rollout_slices", "futbol_rollout_slices", "futbol_rollout_kernel",
-           "futbol_set_rollout_variant", "futbol_gather_minibatch")
+           "futbol_set_rollout_variant", "futbol_gather_minibatch", "futbol_sample_actions")
 
 _lib = None
 
@@ -112,6 +112,8 @@ def load():
     L.futbol_rollout_kernel.argtypes = [vp, C.c_int]
     L.futbol_set_rollout_variant.restype = C.c_int
     L.futbol_set_rollout_variant.argtypes = [vp, C.c_int]
+    L.futbol_sample_actions.restype = C.c_int
+    L.futbol_sample_actions.argtypes = [vp, C.c_int, C.c_int64, C.c_int, C.c_uint64, vp, C.c_uint64, vp, vp, vp]
     L.futbol_gather_minibatch.restype = C.c_int
     L.futbol_gather_minibatch.argtypes = [vp, C.c_int64, C.c_int64, vp, C.c_int, vp] + [vp] * 10 + [vp, vp]
     L.futbol_launch_count.restype = C.c_uint64

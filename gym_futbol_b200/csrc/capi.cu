@@ -17,6 +17,8 @@ cudaError_t launch_gather_minibatch(const long long *idx, long long m, long long
                                     const uint8_t *act, uint8_t *act_out, const float *c0, float *c0_out, const float *c1,
                                     float *c1_out, const float *c2, float *c2_out, const float *c3, float *c3_out,
                                     unsigned long long *bad, cudaStream_t st);
+cudaError_t launch_sample_actions(const void *logits, int bf16, long long n, int n_actions, unsigned long long seed,
+                                  const unsigned long long *t_base, unsigned long long t_off, uint8_t *actions, float *logp, cudaStream_t st);
 cudaError_t launch_gae(const float *reward, const uint8_t *done, const float *value, float gamma, float lam, float *adv,
                        float *ret, int T, int n, cudaStream_t st);
 }
@@ -290,6 +292,18 @@ int futbol_gather_minibatch(const int64_t *idx, int64_t m, int64_t rows, const f
     if (obs != nullptr && obs_dim <= 0) return fail(FUTBOL_ERR_ARG, "obs_dim must be positive%s");
     cudaError_t e = launch_gather_minibatch((const long long *)idx, m, rows, obs, obs_dim, obs_out, act, act_out, c0, c0_out, c1, c1_out,
                                             c2, c2_out, c3, c3_out, (unsigned long long *)bad, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e);
+    return FUTBOL_OK;
+}
+
+int futbol_sample_actions(const void *logits, int logits_dtype, int64_t n, int n_actions, uint64_t seed, const uint64_t *t_base,
+                          uint64_t t_off, uint8_t *actions, float *logp, void *stream)
+{
+    if (logits == nullptr || actions == nullptr) return fail(FUTBOL_ERR_ARG, "null logits or actions%s");
+    if (logits_dtype != 0 && logits_dtype != 1) return fail(FUTBOL_ERR_ARG, "logits_dtype must be 0 (f32) or 1 (bf16)%s");
+    if (n <= 0 || n_actions < 1 || n_actions > 32) return fail(FUTBOL_ERR_ARG, "n must be positive and n_actions in 1..32%s");
+    cudaError_t e = launch_sample_actions(logits, logits_dtype, n, n_actions, seed, (const unsigned long long *)t_base, t_off, actions, logp,
+                                          (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e);
     return FUTBOL_OK;
 }

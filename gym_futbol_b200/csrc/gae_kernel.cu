@@ -7,7 +7,9 @@
 // elements.  HBM-bound: 4 (r) + 1 (done) + 4 (V) read, 8 written per element = 17 bytes.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cuda_bf16.h>
 #include "../../include/futbol_b200.h"
+#include "philox.cuh"
 
 namespace futbol {
 
@@ -73,6 +75,55 @@ cudaError_t launch_gather_minibatch(const long long *idx, long long m, long long
     if (blocks > 148 * 64) blocks = 148 * 64;
     gather_minibatch_kernel<<<(int)blocks, 256, 0, st>>>(idx, m, rows, obs, obs_dim, obs_out, act, act_out, c0, c0_out, c1, c1_out,
                                                          c2, c2_out, c3, c3_out, bad);
+    return cudaGetLastError();
+}
+
+// Categorical sampling between the policy's forward pass and futbol_step: what stable-baselines'
+// CategoricalProbabilityDistribution.sample() / .neglogp() do for the reference's Discrete(16) action space
+// (colab_notebook.ipynb:852 runner; envs/futbol_env.py:143), as ONE launch instead of softmax + multinomial + gather + cast.
+// One thread per row: m = max l, s = sum exp(l - m), u = a 24-bit Philox uniform of (seed, *t_base + t_off, row), action = the
+// first k whose running sum of exp(l - m) exceeds u s (the last action with a non-zero term if rounding never lets it),
+// logp = l[k] - m - log s.  The row (n_actions <= 32 values) is read three times; the second and third pass hit L1.
+constexpr uint32_t kStreamSampler = 4;
+template <typename T> __device__ __forceinline__ float logit_at(const T *p, int k);
+template <> __device__ __forceinline__ float logit_at<float>(const float *p, int k) { return __ldg(p + k); }
+template <> __device__ __forceinline__ float logit_at<__nv_bfloat16>(const __nv_bfloat16 *p, int k) { return __bfloat162float(p[k]); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) sample_actions_kernel(const T *__restrict__ logits, long long n, int n_actions, PhiloxKey key,
+                                                             const unsigned long long *__restrict__ t_base, unsigned long long t_off,
+                                                             uint8_t *__restrict__ actions, float *__restrict__ logp)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T *row = logits + i * n_actions;
+    float m = logit_at(row, 0);
+    for (int k = 1; k < n_actions; ++k) m = fmaxf(m, logit_at(row, k));
+    float s = 0.0f;
+    for (int k = 0; k < n_actions; ++k) s += expf(logit_at(row, k) - m);
+    const unsigned long long t = (t_base != nullptr ? *t_base : 0ull) + t_off;
+    const Philox4 r = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)i, kStreamSampler ^ ((uint32_t)((unsigned long long)i >> 32) << 8), key);
+    const float target = (float)(r.x >> 8) * (1.0f / 16777216.0f) * s;
+    int pick = 0;
+    float run = 0.0f, lp = logit_at(row, 0);
+    bool found = false;
+    for (int k = 0; k < n_actions; ++k) {
+        const float l = logit_at(row, k), e = expf(l - m);
+        run += e;
+        if (!found && e > 0.0f) { pick = k; lp = l; }          // the last action with a non-zero term so far
+        if (!found && run > target) found = true;
+    }
+    actions[i] = (uint8_t)pick;
+    if (logp != nullptr) logp[i] = lp - m - logf(s);
+}
+
+cudaError_t launch_sample_actions(const void *logits, int bf16, long long n, int n_actions, unsigned long long seed,
+                                  const unsigned long long *t_base, unsigned long long t_off, uint8_t *actions, float *logp, cudaStream_t st)
+{
+    const PhiloxKey key = philox_expand_key(seed);
+    const int blocks = (int)((n + 255) / 256);
+    if (bf16) sample_actions_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16 *)logits, n, n_actions, key, t_base, t_off, actions, logp);
+    else sample_actions_kernel<float><<<blocks, 256, 0, st>>>((const float *)logits, n, n_actions, key, t_base, t_off, actions, logp);
     return cudaGetLastError();
 }
 

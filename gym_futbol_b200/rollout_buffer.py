@@ -1,5 +1,5 @@
-"""Rollout-buffer glue behind the simulator: generalised advantage estimation (futbol_gae) and the minibatch gather
-(futbol_gather_minibatch) on the device.
+"""Rollout-buffer glue around the simulator: action sampling from the policy's logits (futbol_sample_actions), generalised
+advantage estimation (futbol_gae) and the minibatch gather (futbol_gather_minibatch) on the device.
 
 Mirrors what stable-baselines' PPO2 runner does with the reference env's outputs (colab_notebook.ipynb:852;
 gamma 0.99 / lambda 0.95 in the saved models' JSON), on the ``[T, n]`` tensors the vectorised env produces,
@@ -31,6 +31,33 @@ def gae(reward, done, value, gamma=0.99, lam=0.95, out=None):
         _lib.check(lib.futbol_gae(C.c_void_p(reward.data_ptr()), C.c_void_p(done.data_ptr()), C.c_void_p(value.data_ptr()),
                                   float(gamma), float(lam), C.c_void_p(adv.data_ptr()), C.c_void_p(ret.data_ptr()), T, n, stream))
     return adv, ret
+
+
+def sample_actions(logits, seed=0, t=0, t_base=None, out=None):
+    """One categorical draw per row of ``logits`` ([n, A] float32 or bfloat16 CUDA tensor, A <= 32) in ONE launch:
+    returns ``(actions uint8 [n], log_prob float32 [n])`` -- what softmax + multinomial + gather + cast compute.  The
+    uniform of row i is Philox(seed, t_base[0] + t, i): ``t_base`` is an optional one-element int64 CUDA tensor, a counter
+    the caller advances (``t_base += T``) so that a captured CUDA graph draws fresh numbers on every replay."""
+    if not logits.is_cuda:
+        raise _lib.FutbolError("sample_actions needs CUDA tensors; there is no CPU fallback")
+    if logits.dim() != 2 or logits.dtype not in (torch.float32, torch.bfloat16) or not 1 <= logits.shape[1] <= 32:
+        raise ValueError("logits must be [n, A] float32 or bfloat16 with A <= 32")
+    if t_base is not None and (t_base.dtype != torch.int64 or t_base.numel() != 1 or t_base.device != logits.device):
+        raise ValueError("t_base must be a one-element int64 tensor on the logits' device")
+    logits = logits.contiguous()
+    n, A = logits.shape
+    act, logp = out if out is not None else (torch.empty(n, dtype=torch.uint8, device=logits.device),
+                                             torch.empty(n, dtype=torch.float32, device=logits.device))
+    if act.dtype != torch.uint8 or logp.dtype != torch.float32 or act.numel() != n or logp.numel() != n or not (
+            act.is_contiguous() and logp.is_contiguous()) or act.device != logits.device or logp.device != logits.device:
+        raise ValueError("out must be (uint8 [n], float32 [n]), contiguous, on the logits' device")
+    lib = _lib.load()
+    with torch.cuda.device(logits.device):
+        stream = C.c_void_p(torch.cuda.current_stream(logits.device).cuda_stream)
+        _lib.check(lib.futbol_sample_actions(C.c_void_p(logits.data_ptr()), 1 if logits.dtype == torch.bfloat16 else 0, n, A,
+                                             int(seed) & (2 ** 64 - 1), None if t_base is None else C.c_void_p(t_base.data_ptr()),
+                                             int(t), C.c_void_p(act.data_ptr()), C.c_void_p(logp.data_ptr()), stream))
+    return act, logp
 
 
 def gather_minibatch(obs, idx, act=None, cols=(), out=None):

@@ -166,6 +166,18 @@ int futbol_gather_minibatch(const int64_t *idx, int64_t m, int64_t rows, const f
                             const uint8_t *act, uint8_t *act_out, const float *c0, float *c0_out, const float *c1, float *c1_out,
                             const float *c2, float *c2_out, const float *c3, float *c3_out, uint64_t *bad, void *stream);
 
+/* ---- rollout-buffer glue: action sampling -------------------------------------------------------
+ * One categorical draw per row of unnormalised log-probabilities, in one launch: what stable-baselines'
+ * CategoricalProbabilityDistribution.sample() and .neglogp() compute between the policy's forward pass and env.step for
+ * the reference's Discrete(16) action space (envs/futbol_env.py:143; runner: colab_notebook.ipynb:852).
+ * logits [n, n_actions] row-major, float32 (logits_dtype 0) or bfloat16 (1), 1 <= n_actions <= 32, finite.
+ * u = 24-bit uniform from Philox4x32-10 (key seed, counter (t, row), stream 4) with t = (*t_base if t_base else 0) + t_off:
+ * t_base is a DEVICE counter, so a captured CUDA graph draws fresh numbers on every replay once the caller advances it.
+ * action[i] = the first k with sum_{j<=k} exp(l_j - max l) > u * sum_j exp(l_j - max l); logp[i] (may be NULL) =
+ * log-softmax(l)[action].  actions uint8 [n], logp float32 [n].  No handle. */
+int futbol_sample_actions(const void *logits, int logits_dtype, int64_t n, int n_actions, uint64_t seed, const uint64_t *t_base,
+                          uint64_t t_off, uint8_t *actions, float *logp, void *stream);
+
 /* ---- self test ----------------------------------------------------------------------------
  * Compares the kernel's guard-free fp64 division / square-root sequences (csrc/ieee_fast.cuh) with the
  * compiler's __ddiv_rn / __dsqrt_rn on n operand pairs: a[i] / b[i], (a[i], |b[i]|) / b[i] through the

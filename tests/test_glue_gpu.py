@@ -156,7 +156,7 @@ def test_ppo_example_fused_equals_unfused(torch_cuda):
     spec.loader.exec_module(mod)
     runs = []
     for fused in (True, False):
-        ppo = mod.PPO(n_envs=512, n_steps=16, minibatches=2, epochs=1, seed=1, bf16=False, fused=fused, graph=False)
+        ppo = mod.PPO(n_envs=512, n_steps=16, minibatches=2, epochs=1, seed=1, bf16=False, fused=fused, graph=False, sampler="torch")
         torch.manual_seed(5)
         ppo.collect()
         ppo.collect()                                          # the second collection continues from the first
@@ -192,3 +192,94 @@ def test_host_rollout_delivers_the_device_rollout(torch_cuda):
     assert host_io.measure_d2h_peak("cuda:0", nbytes=1 << 24, reps=1) > 0.1
     cpus = host_io.gpu_local_cpus(0)
     assert cpus is None or len(cpus) >= 1
+
+
+def _sampler_uniforms(seed, t, n):
+    from oracle import philox
+    k0, k1 = philox.seed_key(seed)
+    w = philox.philox4x32_10_np(np.full(n, t & 0xFFFFFFFF, np.uint64), np.full(n, t >> 32, np.uint64), np.arange(n, dtype=np.uint64),
+                                np.full(n, 4, np.uint64), k0, k1)[0]
+    return (w >> np.uint64(8)).astype(np.float64) / 16777216.0
+
+
+def test_sample_actions_follows_its_rule(torch_cuda):
+    """futbol_sample_actions against a float64 restatement of its rule with the same Philox uniforms (oracle/philox.py), and
+    its log-probabilities against torch's log_softmax; bf16 logits; the device counter."""
+    torch = torch_cuda
+    from gym_futbol_b200.rollout_buffer import sample_actions
+    n, A, seed, t = 20000, 16, 77, (5 << 32) + 123
+    g = torch.Generator(device="cuda").manual_seed(3)
+    logits = torch.randn(n, A, device="cuda", generator=g) * 3.0
+    logits[:50, 3] = -200.0                                     # terms that underflow to zero are never picked
+    logits[50:60] = 0.0
+    act, logp = sample_actions(logits, seed=seed, t=t)
+    torch.cuda.synchronize()
+    l = logits.double().cpu().numpy()
+    e = np.exp(l - l.max(1, keepdims=True))
+    cum, tot = np.cumsum(e, 1), e.sum(1)
+    target = _sampler_uniforms(seed, t, n) * tot
+    a = act.cpu().numpy().astype(np.int64)
+    rows = np.arange(n)
+    lo = np.where(a > 0, cum[rows, np.maximum(a - 1, 0)], 0.0)
+    eps = 1e-5 * tot                                            # the kernel sums in float32
+    assert np.all(lo <= target + eps) and np.all(cum[rows, a] > target - eps)
+    exact = np.argmax(cum > target[:, None], 1)
+    assert np.mean(exact == a) > 0.999                          # away from the float32 rounding band the pick IS the rule's
+    assert not np.any(a[:50] == 3)
+    want = torch.log_softmax(logits, -1).gather(1, act.long().unsqueeze(1)).squeeze(1)
+    assert torch.allclose(logp, want, atol=2e-5, rtol=0)
+    # bf16 logits: the same picks as float32 logits holding the same values
+    lb = logits.to(torch.bfloat16)
+    a_b, lp_b = sample_actions(lb, seed=seed, t=t)
+    a_f, lp_f = sample_actions(lb.float(), seed=seed, t=t)
+    assert torch.equal(a_b, a_f) and torch.equal(lp_b, lp_f)
+    # the device counter: t_base + t_off is the draw's t; out= buffers
+    base = torch.tensor([t - 7], dtype=torch.int64, device="cuda")
+    out = (torch.empty(n, dtype=torch.uint8, device="cuda"), torch.empty(n, device="cuda"))
+    a2, lp2 = sample_actions(logits, seed=seed, t=7, t_base=base, out=out)
+    assert a2.data_ptr() == out[0].data_ptr() and torch.equal(a2, act) and torch.equal(lp2, logp)
+    assert not torch.equal(sample_actions(logits, seed=seed, t=t + 1)[0], act)
+    with pytest.raises(ValueError):
+        sample_actions(torch.zeros(4, 33, device="cuda"))
+
+
+def test_sample_actions_distribution(torch_cuda):
+    """400,000 draws from one softmax: every frequency within five standard deviations."""
+    torch = torch_cuda
+    from gym_futbol_b200.rollout_buffer import sample_actions
+    n = 400000
+    row = torch.tensor([0.3, -1.0, 2.0, 0.0, -4.0, 1.5, 0.7, -0.2, 1.1, -2.5, 0.0, 0.9, -0.6, 2.2, -1.7, 0.4], device="cuda")
+    act, _ = sample_actions(row.repeat(n, 1), seed=5, t=9)
+    p = torch.softmax(row.double(), 0).cpu().numpy()
+    freq = np.bincount(act.cpu().numpy(), minlength=16) / n
+    assert np.all(np.abs(freq - p) < 5 * np.sqrt(p * (1 - p) / n))
+
+
+def test_ppo_example_kernel_sampler_and_graph(torch_cuda):
+    """The fused flow with futbol_sample_actions, eager and as a CUDA graph: the graph replay draws fresh numbers (device
+    counter), the stored log-probabilities are those of the stored actions, and the update gives a finite loss."""
+    import importlib.util
+    import os
+    torch = torch_cuda
+    spec = importlib.util.spec_from_file_location("ppo_v0", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "ppo_v0.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ppo = mod.PPO(n_envs=1024, n_steps=8, minibatches=2, epochs=1, seed=2, bf16=False, fused=True, graph=True)
+    assert ppo.sampler == "kernel"
+    ppo.collect()
+    a0 = ppo.act_buf.clone()
+    with torch.no_grad():
+        logits, _ = ppo.policy(ppo.obs_buf[3])
+    want = torch.log_softmax(logits.float(), -1).gather(1, ppo.act_buf[3].long().unsqueeze(1)).squeeze(1)
+    assert torch.allclose(ppo.logp_buf[3], want, atol=1e-4)
+    ppo.prepare_graph()
+    assert ppo.graph is not None
+    ppo.collect()
+    a1 = ppo.act_buf.clone()
+    ppo.collect()
+    a2 = ppo.act_buf.clone()
+    torch.cuda.synchronize()
+    assert int(ppo.t_base.item()) == 24 and not torch.equal(a1, a2) and not torch.equal(a0, a1)
+    assert 0.02 < (a1 == a2).float().mean().item() < 0.2       # two replays agree about as often as two uniform draws of 16 would
+    ppo.update()
+    assert torch.isfinite(ppo.last_loss).item()
