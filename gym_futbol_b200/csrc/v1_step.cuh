@@ -364,10 +364,10 @@ __device__ __forceinline__ void solve_contact(Lane L, Contact &k, int ball)
     const double vrn = dadd(dmul(dsub(v2x, L.f(ao + kVX)), k.nx), dmul(dsub(v2y, L.f(ao + kVY)), k.ny));
     const double jbn = dmul(dsub(k.bias, vbn), k.n_mass), jbn_old = k.jbias;
     const double t1 = dadd(jbn_old, jbn);
-    k.jbias = t1 > 0.0 ? t1 : 0.0;
+    k.jbias = pick(t1 > 0.0, t1, 0.0);      // cpfmax(x, 0) as compare + select: the ternary compiles to the NaN-quieting DSETP.MAX sequence
     const double jn = dmul(-dadd(k.bounce, vrn), k.n_mass), jn_old = k.jn;
     const double t2 = dadd(jn_old, jn);
-    k.jn = t2 > 0.0 ? t2 : 0.0;
+    k.jn = pick(t2 > 0.0, t2, 0.0);
     const double db = dsub(k.jbias, jbn_old), dj = dsub(k.jn, jn_old);
     const double bx = dmul(k.nx, db), by = dmul(k.ny, db), jx = dmul(k.nx, dj), jy = dmul(k.ny, dj);
     L.f(ao + kBX) = dsub(L.f(ao + kBX), dmul(bx, ma)); L.f(ao + kBY) = dsub(L.f(ao + kBY), dmul(by, ma));
@@ -516,7 +516,7 @@ __device__ __forceinline__ int space_step(Lane L, V1Regs &s, const V1Params &P, 
                 nm_bs = 1.0 / (m_inv_b + 0.0);
             k.n_mass = b >= 0 ? ((a == ball || b == ball) ? nm_pb : nm_pp) : (a == ball ? nm_bs : nm_ps);
             double m = dadd(pen, kSlop);
-            m = m < 0.0 ? m : 0.0;                                       // cpfmin(0, dist + slop)
+            m = pick(m < 0.0, m, 0.0);                                   // cpfmin(0, dist + slop)
             const double bnum = dmul(-P.bias_coef, m);                   // -0.0 unless the pair overlaps by more than the slop
             const bool bz = bnum == 0.0;
             const double bq = fdiv(pick(bz, 1.0, bnum), kDt);
