@@ -65,6 +65,37 @@ def test_rollout_is_cuda_graph_capturable(torch_cuda):
         assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
 
 
+@pytest.mark.parametrize("variant", ["v0", "v1"])
+def test_time_sliced_rollout_is_cuda_graph_capturable(torch_cuda, variant):
+    """The work-queue launch (a memset of the scheduler words + one kernel) captures and replays like the plain one."""
+    torch = torch_cuda
+    from gym_futbol_b200 import FutbolVecEnv, FutbolV1VecEnv
+    n, K = 3000, 16
+
+    def make():
+        e = FutbolVecEnv(n, seed=5, random_opp=True) if variant == "v0" else FutbolV1VecEnv(n, number_of_player=3, seed=5)
+        e.set_rollout_slices(4)
+        e.reset()
+        return e
+    a, b = make(), make()
+    assert "sliced" in a.rollout_kernel(K)
+    a.rollout(K)                                   # allocate the cached buffers, query the occupancy: outside the capture
+    b.rollout(K)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            oa, ra, da = a.rollout(K)
+    torch.cuda.current_stream().wait_stream(s)
+    for _ in range(3):
+        g.replay()
+        ob, rb, db = b.rollout(K)
+        torch.cuda.synchronize()
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    assert a.get_state().tobytes() == b.get_state().tobytes()
+
+
 def test_step_outputs_are_the_env_buffers(torch_cuda):
     torch = torch_cuda
     from gym_futbol_b200 import FutbolVecEnv
