@@ -128,12 +128,24 @@ class HostRollout:
         return self.h_obs, self.h_reward, self.h_done
 
     def run_resident(self):
-        """The same loop with the results left in HBM for an on-device consumer: host actions in, statistics out."""
+        """The same loop with the results left in HBM for an on-device consumer: host actions in, statistics out.  The
+        upload of chunk c + 1 (copy stream) overlaps the simulation of chunk c; two device action buffers alternate."""
         env, Kc = self.env, self.Kc
         stream = torch.cuda.current_stream(env.device)
-        da = self._d[0][0]
+        if not hasattr(self, "_uploaded"):
+            self._uploaded = [torch.cuda.Event() for _ in range(2)]      # chunk's actions are in HBM (copy stream)
+            self._consumed = [torch.cuda.Event() for _ in range(2)]      # the rollout that read them is done (compute stream)
+        for ev in self._consumed:
+            ev.record(stream)                      # also orders this call behind whatever used the buffers before it
         for c in range(self.chunks):
-            da.copy_(self.h_actions[c * Kc:(c + 1) * Kc], non_blocking=True)
+            b = c & 1
+            da = self._d[b][0]
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self._consumed[b])
+                da.copy_(self.h_actions[c * Kc:(c + 1) * Kc], non_blocking=True)
+                self._uploaded[b].record(self.copy_stream)
+            stream.wait_event(self._uploaded[b])
             env.rollout(Kc, actions=da)
+            self._consumed[b].record(stream)
         self.h_stats.copy_(env.stats, non_blocking=True)
         stream.synchronize()
