@@ -9,7 +9,7 @@
 #include <stdint.h>
 #include <cuda_bf16.h>
 #include "../../include/futbol_b200.h"
-#include "philox.cuh"
+#include "sampler.cuh"
 
 namespace futbol {
 
@@ -78,13 +78,9 @@ cudaError_t launch_gather_minibatch(const long long *idx, long long m, long long
     return cudaGetLastError();
 }
 
-// Categorical sampling between the policy's forward pass and futbol_step: what stable-baselines'
-// CategoricalProbabilityDistribution.sample() / .neglogp() do for the reference's Discrete(16) action space
-// (colab_notebook.ipynb:852 runner; envs/futbol_env.py:143), as ONE launch instead of softmax + multinomial + gather + cast.
-// One thread per row: m = max l, s = sum exp(l - m), u = a 24-bit Philox uniform of (seed, *t_base + t_off, row), action = the
-// first k whose running sum of exp(l - m) exceeds u s (the last action with a non-zero term if rounding never lets it),
-// logp = l[k] - m - log s.  The row (n_actions <= 32 values) is read three times; the second and third pass hit L1.
-constexpr uint32_t kStreamSampler = 4;
+// Categorical sampling between the policy's forward pass and futbol_step (the row rule lives in sampler.cuh, which also
+// compiles for the host: tests/host_shim/sampler_host.cpp): one thread per row, ONE launch instead of softmax + multinomial +
+// gather + cast.  The row (n_actions <= 32 values) is read three times; the second and third pass hit L1.
 template <typename T> __device__ __forceinline__ float logit_at(const T *p, int k);
 template <> __device__ __forceinline__ float logit_at<float>(const float *p, int k) { return __ldg(p + k); }
 template <> __device__ __forceinline__ float logit_at<__nv_bfloat16>(const __nv_bfloat16 *p, int k) { return __bfloat162float(p[k]); }
@@ -97,24 +93,12 @@ __global__ void __launch_bounds__(256) sample_actions_kernel(const T *__restrict
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const T *row = logits + i * n_actions;
-    float m = logit_at(row, 0);
-    for (int k = 1; k < n_actions; ++k) m = fmaxf(m, logit_at(row, k));
-    float s = 0.0f;
-    for (int k = 0; k < n_actions; ++k) s += expf(logit_at(row, k) - m);
     const unsigned long long t = (t_base != nullptr ? *t_base : 0ull) + t_off;
-    const Philox4 r = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)i, kStreamSampler ^ ((uint32_t)((unsigned long long)i >> 32) << 8), key);
-    const float target = (float)(r.x >> 8) * (1.0f / 16777216.0f) * s;
-    int pick = 0;
-    float run = 0.0f, lp = logit_at(row, 0);
-    bool found = false;
-    for (int k = 0; k < n_actions; ++k) {
-        const float l = logit_at(row, k), e = expf(l - m);
-        run += e;
-        if (!found && e > 0.0f) { pick = k; lp = l; }          // the last action with a non-zero term so far
-        if (!found && run > target) found = true;
-    }
+    int pick;
+    float lp;
+    sample_row([row](int k) { return logit_at(row, k); }, n_actions, key, t, (unsigned long long)i, pick, lp);
     actions[i] = (uint8_t)pick;
-    if (logp != nullptr) logp[i] = lp - m - logf(s);
+    if (logp != nullptr) logp[i] = lp;
 }
 
 cudaError_t launch_sample_actions(const void *logits, int bf16, long long n, int n_actions, unsigned long long seed,
