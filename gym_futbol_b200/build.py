@@ -13,7 +13,8 @@ import sys
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libfutbol_b200.so")
 SOURCES = ("capi.cu", "v0_kernels.cu", "v1_kernels.cu", "gae_kernel.cu", "selftest.cu")
-HEADERS = ("philox.cuh", "v0_step.cuh", "v0_kernels.h", "v1_step.cuh", "v1_kernels.h", "ieee_fast.cuh", os.path.join("..", "..", "include", "futbol_b200.h", "sampler.cuh"))
+HEADERS = ("philox.cuh", "v0_step.cuh", "v0_kernels.h", "v1_step.cuh", "v1_kernels.h", "ieee_fast.cuh", "sampler.cuh",
+           os.path.join("..", "..", "include", "futbol_b200.h"))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
